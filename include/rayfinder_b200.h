@@ -1,0 +1,363 @@
+/*
+ * rayfinder_b200 — C-ABI of the B200-native render path.
+ *
+ * This header is the drop-in boundary for the reference's render path (Nelarius/rayfinder @ 634128c).
+ * The reference has no FFI layer: the path sits behind one C++ class (nlrs::ReferencePathTracer) and
+ * one free function (nlrs::rayIntersectBvh).  Every entry point below names the reference interface
+ * it replaces (paths relative to the reference's src/).  All structs are plain C PODs whose byte
+ * layout equals the reference struct they mirror, so a maintainer can reinterpret_cast spans of the
+ * reference's own containers.
+ *
+ * Conventions: every function returns rf_status (0 = ok) unless it is a pure getter; on failure
+ * rf_last_error() returns a thread-local, NUL-terminated message (the reference throws
+ * std::runtime_error with the same text where one exists).  Handles are opaque and, like the
+ * reference objects, not thread-safe.  There is NO CPU fallback: creating a renderer or a traversal
+ * scene without a CUDA device fails with RF_ERROR_CUDA.
+ */
+#ifndef RAYFINDER_B200_H
+#define RAYFINDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t rf_status;
+enum
+{
+    RF_OK = 0,
+    RF_ERROR_INVALID_ARGUMENT = 1,
+    RF_ERROR_CUDA = 2,
+    RF_ERROR_IO = 3,
+    RF_ERROR_FORMAT = 4,       /* .pt magic/version errors (pt-format/pt_format.cpp:277-291) */
+    RF_ERROR_OUT_OF_RANGE = 5, /* sky params out of range (hw-skymodel/hw_skymodel.c:148-161) */
+};
+
+const char* rf_last_error(void);
+
+/* ---- POD mirrors of the reference's scene structs --------------------------------------------- */
+
+/* nlrs::BvhNode, common/bvh.hpp:13-21 (48 B; Aabb = common/aabb.hpp:12-27). */
+typedef struct rf_bvh_node
+{
+    float    aabb_min[3];
+    float    pad0;
+    float    aabb_max[3];
+    float    pad1;
+    uint32_t triangles_offset;
+    uint32_t second_child_offset;
+    uint32_t triangle_count;
+    uint32_t split_axis;
+} rf_bvh_node;
+
+/* nlrs::Positions, common/triangle_attributes.hpp:7-12 (36 B, CPU-side triangle). */
+typedef struct rf_positions
+{
+    float v0[3];
+    float v1[3];
+    float v2[3];
+} rf_positions;
+
+/* nlrs::PositionAttribute, pt-format/vertex_attributes.hpp:7-15 (48 B). */
+typedef struct rf_position_attribute
+{
+    float p0[3];
+    float pad0;
+    float p1[3];
+    float pad1;
+    float p2[3];
+    float pad2;
+} rf_position_attribute;
+
+/* nlrs::VertexAttributes, pt-format/vertex_attributes.hpp:17-35 (80 B). */
+typedef struct rf_vertex_attributes
+{
+    float    n0[3];
+    float    pad0;
+    float    n1[3];
+    float    pad1;
+    float    n2[3];
+    float    pad2;
+    float    uv0[2];
+    float    uv1[2];
+    float    uv2[2];
+    uint32_t texture_idx;
+    uint32_t pad3;
+} rf_vertex_attributes;
+
+/* nlrs::Texture, common/texture.hpp:10-49: BGRA8 pixels (b | g<<8 | r<<16 | a<<24), row-major. */
+typedef struct rf_texture
+{
+    const uint32_t* pixels;
+    uint32_t        width;
+    uint32_t        height;
+} rf_texture;
+
+/* nlrs::Scene, pt/reference_path_tracer.hpp:45-51: four non-owning spans.  Data is copied to the
+ * device inside rf_renderer_create; the caller may free it afterwards (as pt/main.cpp:176-177 does). */
+typedef struct rf_scene
+{
+    const rf_bvh_node*           bvh_nodes;
+    uint64_t                     num_bvh_nodes;
+    const rf_position_attribute* position_attributes;
+    uint64_t                     num_position_attributes;
+    const rf_vertex_attributes*  vertex_attributes;
+    uint64_t                     num_vertex_attributes;
+    const rf_texture*            base_color_textures;
+    uint64_t                     num_base_color_textures;
+} rf_scene;
+
+/* nlrs::Camera, common/camera.hpp:10-21 (19 floats). */
+typedef struct rf_camera
+{
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float up[3];
+    float right[3];
+    float lens_radius;
+} rf_camera;
+
+/* nlrs::SamplingParams, pt/reference_path_tracer.hpp:26-32 (defaults 128 / 4). */
+typedef struct rf_sampling_params
+{
+    uint32_t num_samples_per_pixel;
+    uint32_t num_bounces;
+} rf_sampling_params;
+
+/* nlrs::Sky, pt/aligned_sky_state.hpp:15-23 (defaults 1, {1,1,1}, 30, 0). */
+typedef struct rf_sky
+{
+    float turbidity;
+    float albedo[3];
+    float sun_zenith_degrees;
+    float sun_azimuth_degrees;
+} rf_sky;
+
+/* nlrs::RenderParameters, pt/reference_path_tracer.hpp:34-43. */
+typedef struct rf_render_parameters
+{
+    uint32_t           framebuffer_width;
+    uint32_t           framebuffer_height;
+    rf_camera          camera;
+    rf_sampling_params sampling_params;
+    rf_sky             sky;
+    float              exposure;
+} rf_render_parameters;
+
+/* nlrs::RendererDescriptor, pt/reference_path_tracer.hpp:53-57. */
+typedef struct rf_renderer_descriptor
+{
+    rf_render_parameters render_params;
+    int32_t              max_framebuffer_width;
+    int32_t              max_framebuffer_height;
+} rf_renderer_descriptor;
+
+/* nlrs::AlignedSkyState, pt/aligned_sky_state.hpp:34-41 (160 B, the block the WGSL reads). */
+typedef struct rf_sky_state
+{
+    float params[27];
+    float sky_radiances[3];
+    float solar_radiances[3];
+    float padding1[3];
+    float sun_direction[3];
+    float padding2;
+} rf_sky_state;
+
+/* Work counters of the frames rendered since the last rf_renderer_reset_stats (new: the reference
+ * only records the render-pass duration, pt/reference_path_tracer.cpp:668-716).  A "ray" is one
+ * call of the reference's rayIntersectBvh (wgsl:190) or shadowRay (wgsl:202). */
+typedef struct rf_frame_stats
+{
+    uint64_t frames;
+    uint64_t paths;                /* primary rays generated */
+    uint64_t closest_rays;         /* rayIntersectBvh calls */
+    uint64_t shadow_rays;          /* shadowRay calls */
+    uint64_t closest_nodes_visited;
+    uint64_t closest_triangles_tested;
+    uint64_t shadow_nodes_visited;
+    uint64_t shadow_triangles_tested;
+    double   device_ms_total;      /* CUDA-event time of the render passes */
+    double   device_ms_closest;    /* per-stage CUDA-event time, only filled when stage timing is on */
+    double   device_ms_shadow;
+    double   device_ms_shade;
+    double   device_ms_other;
+} rf_frame_stats;
+
+/* ---- the renderer: nlrs::ReferencePathTracer (pt/reference_path_tracer.hpp:59-102) ------------- */
+
+typedef struct rf_renderer rf_renderer;
+
+/* ReferencePathTracer(const RendererDescriptor&, const GpuContext&, Scene)
+ * (reference_path_tracer.cpp:131-481).  `device` < 0 selects the current CUDA device; the
+ * GpuContext argument has no analogue.  Fails with the reference's message when the texture data
+ * exceeds the 1 GiB binding limit (reference_path_tracer.cpp:256-263, pt/gpu_limits.hpp:20-25). */
+rf_status rf_renderer_create(
+    const rf_renderer_descriptor* desc,
+    const rf_scene*               scene,
+    int32_t                       device,
+    rf_renderer**                 out);
+
+/* ~ReferencePathTracer (reference_path_tracer.cpp:548-554). */
+void rf_renderer_destroy(rf_renderer* r);
+
+/* setRenderParameters (reference_path_tracer.cpp:556-563): any change resets the accumulation. */
+rf_status rf_renderer_set_render_parameters(rf_renderer* r, const rf_render_parameters* params);
+
+/* render (reference_path_tracer.cpp:565-704): one sample per pixel is traced and added to the HDR
+ * accumulation buffer when accumulated < numSamplesPerPixel; frameCount always advances.  The
+ * swap-chain / ImGui arguments have no analogue; the tonemapped image is read with
+ * rf_renderer_read_display.  Asynchronous on the renderer's stream. */
+rf_status rf_renderer_render(rf_renderer* r);
+
+/* averageRenderpassDurationMs (reference_path_tracer.cpp:706-716): mean of the last <= 30 passes. */
+float rf_renderer_average_renderpass_duration_ms(rf_renderer* r);
+/* renderProgressPercentage (reference_path_tracer.cpp:718-722). */
+float rf_renderer_render_progress_percentage(const rf_renderer* r);
+
+/* New (the reference never reads its image back): copy the accumulated HDR *sum* buffer
+ * `imageBuffer: array<vec3f>` (wgsl:32; 16-byte stride, W*H*4 floats, row 0 = top) to host memory
+ * and return the sample count it holds. Synchronises the stream. */
+rf_status rf_renderer_read_hdr(rf_renderer* r, float* dst_rgba, uint64_t num_floats, uint32_t* accumulated);
+/* The display transform of fsMain (wgsl:59-63): estimator = sum/acc, acesFilmic(exposure*x),
+ * pow(1/2.2), packed BGRA8 (the reference's swap-chain format), W*H u32. */
+rf_status rf_renderer_read_display(rf_renderer* r, uint32_t* dst_bgra8, uint64_t num_pixels);
+
+/* Device-side access for multi-GPU reduction and zero-copy consumers. */
+void*     rf_renderer_hdr_device_ptr(rf_renderer* r);       /* float4[max_w*max_h] */
+rf_status rf_renderer_set_stream(rf_renderer* r, void* cuda_stream);
+rf_status rf_renderer_synchronize(rf_renderer* r);
+
+/* The reference's frame counter (mFrameCount, reference_path_tracer.cpp:580) is the "seed" of the
+ * blue-noise/R2 sequence (wgsl:603-616); expose it so runs are reproducible. */
+rf_status rf_renderer_set_frame_count(rf_renderer* r, uint32_t frame_count);
+uint32_t  rf_renderer_frame_count(const rf_renderer* r);
+uint32_t  rf_renderer_accumulated_sample_count(const rf_renderer* r);
+
+/* Multi-GPU: this renderer traces only the 32x32-pixel tiles t=(tx,ty) with (tx+ty) % world == rank
+ * and leaves every other pixel of the HDR buffer exactly 0, so a sum-reduce over ranks is
+ * bit-identical to a single-GPU frame.  Resets the accumulation. */
+rf_status rf_renderer_set_tile_partition(rf_renderer* r, uint32_t rank, uint32_t world);
+
+rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out);
+rf_status rf_renderer_reset_stats(rf_renderer* r);
+/* Per-stage CUDA-event timing (adds event records between stages; off by default). */
+rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled);
+
+/* ---- the CPU traversal twin: nlrs::rayIntersectBvh (common/ray_intersection.hpp:43-49) --------- */
+
+typedef struct rf_traversal_scene rf_traversal_scene;
+
+/* Uploads (bvhNodes, triangles) as passed to rayIntersectBvh by bvh-visualizer/main.cpp:71,
+ * pt/main.cpp:217 and tests/bvh.cpp:92. */
+rf_status rf_traversal_scene_create(
+    const rf_bvh_node*   bvh_nodes,
+    uint64_t             num_bvh_nodes,
+    const rf_positions*  triangles,
+    uint64_t             num_triangles,
+    int32_t              device,
+    rf_traversal_scene** out);
+void rf_traversal_scene_destroy(rf_traversal_scene* s);
+
+/* Batched rayIntersectBvh (ray_intersection.cpp:138-213) on host buffers.  rays: n x 6 floats
+ * (origin, direction).  Outputs (each may be NULL): out_hit n x u8 (the bool result); out_p_t n x 4
+ * floats = Intersection{p, t} (ray_intersection.hpp:15-19; zeros on miss); out_nodes_visited n x u32 =
+ * BvhStats::nodesVisited (:37-40). */
+rf_status rf_ray_intersect_bvh(
+    rf_traversal_scene* s,
+    const float*        rays,
+    uint64_t            num_rays,
+    float               ray_t_max,
+    uint8_t*            out_hit,
+    float*              out_p_t,
+    uint32_t*           out_nodes_visited);
+
+/* The pixel loop of bvh-visualizer/main.cpp:60-78: u = j/W, v = 1-(i+1)/H, generateCameraRay
+ * (camera.cpp:44-51), rayIntersectBvh(..., ray_t_max, ...); out_nodes_visited is W*H u32, row-major,
+ * row 0 = top.  `device_ms` (may be NULL) receives the kernel time. */
+rf_status rf_bvh_visualizer_node_counts(
+    rf_traversal_scene* s,
+    const rf_camera*    camera,
+    uint32_t            width,
+    uint32_t            height,
+    float               ray_t_max,
+    uint32_t*           out_nodes_visited,
+    float*              device_ms);
+
+/* ---- host-side pieces the path keeps (no GPU needed) ------------------------------------------- */
+
+/* createCamera (common/camera.cpp:7-42). vfov in radians (Angle::asRadians). */
+rf_status rf_create_camera(
+    const float origin[3],
+    const float look_at[3],
+    float       aperture,
+    float       focus_distance,
+    float       vfov_radians,
+    float       aspect_ratio,
+    rf_camera*  out);
+
+/* AlignedSkyState(const Sky&) (pt/aligned_sky_state.hpp:43-70) on top of sky_state_new
+ * (hw-skymodel/hw_skymodel.c:141-180).  Returns RF_ERROR_OUT_OF_RANGE (with the failing field named
+ * in rf_last_error) where sky_state_new returns a non-success sky_state_result. */
+rf_status rf_sky_state_new(const rf_sky* sky, rf_sky_state* out);
+
+/* buildBvh (common/bvh.cpp:263-291).  out_nodes needs room for 2*n-1 nodes; out_triangle_indices
+ * (n x u64) is Bvh::triangleIndices (old index -> new index, common/bvh.hpp:24-28). */
+rf_status rf_build_bvh(
+    const rf_positions* triangles,
+    uint64_t            num_triangles,
+    rf_bvh_node*        out_nodes,
+    uint64_t*           out_num_nodes,
+    uint64_t*           out_triangle_indices);
+
+/* ---- .pt container: nlrs::PtFormat + serialize/deserialize (pt-format/pt_format.hpp:18-43) ----- */
+
+typedef struct rf_pt_file rf_pt_file;
+
+enum
+{
+    RF_PT_BVH_NODES = 0,                      /* 48 B  */
+    RF_PT_BVH_POSITION_ATTRIBUTES = 1,        /* 36 B  nlrs::Positions */
+    RF_PT_TRIANGLE_POSITION_ATTRIBUTES = 2,   /* 48 B  */
+    RF_PT_TRIANGLE_VERTEX_ATTRIBUTES = 3,     /* 80 B  */
+    RF_PT_VERTEX_POSITIONS = 4,               /* 16 B vec4 */
+    RF_PT_VERTEX_NORMALS = 5,                 /* 16 B vec4 */
+    RF_PT_VERTEX_TEX_COORDS = 6,              /* 8 B vec2 */
+    RF_PT_VERTEX_INDICES = 7,                 /* 4 B */
+    RF_PT_MODEL_VERTEX_POSITIONS = 8,         /* slices: 16 B {u64 offsetIdx, u64 numElements} */
+    RF_PT_MODEL_VERTEX_NORMALS = 9,
+    RF_PT_MODEL_VERTEX_TEX_COORDS = 10,
+    RF_PT_MODEL_VERTEX_INDICES = 11,
+    RF_PT_MODEL_BASE_COLOR_TEXTURE_INDICES = 12, /* 4 B */
+    RF_PT_NUM_ARRAYS = 13,
+};
+
+rf_status rf_pt_create(rf_pt_file** out);  /* PtFormat() = default */
+void      rf_pt_destroy(rf_pt_file* f);
+/* deserialize(InputStream&, PtFormat&) (pt_format.cpp:271-321) from a file / a memory buffer. */
+rf_status rf_pt_load(const char* path, rf_pt_file** out);
+rf_status rf_pt_load_memory(const void* data, uint64_t size, rf_pt_file** out);
+/* serialize(OutputStream&, const PtFormat&) (pt_format.cpp:240-269). */
+rf_status rf_pt_save(const rf_pt_file* f, const char* path);
+rf_status rf_pt_save_memory(const rf_pt_file* f, void* dst, uint64_t capacity, uint64_t* size);
+/* Array access: element count, element size and a pointer valid until the file is modified. */
+rf_status rf_pt_array(const rf_pt_file* f, int32_t which, const void** data, uint64_t* count, uint64_t* elem_size);
+rf_status rf_pt_set_array(rf_pt_file* f, int32_t which, const void* data, uint64_t count);
+uint64_t  rf_pt_num_textures(const rf_pt_file* f);
+rf_status rf_pt_texture(const rf_pt_file* f, uint64_t idx, rf_texture* out);
+rf_status rf_pt_add_texture(rf_pt_file* f, const uint32_t* pixels, uint32_t width, uint32_t height);
+/* Fill an rf_scene (the four spans of pt/main.cpp:150-155) pointing into `f`; `textures` must have
+ * room for rf_pt_num_textures(f) entries. */
+rf_status rf_pt_scene(const rf_pt_file* f, rf_scene* out, rf_texture* textures);
+
+/* Introspection used by the tests / bench: 1 when built with CUDA kernels for sm_100a. */
+int32_t     rf_has_cuda_kernels(void);
+const char* rf_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYFINDER_B200_H */

@@ -1,0 +1,762 @@
+// Host driver of the CUDA render path + its C-ABI: the counterpart of
+// nlrs::ReferencePathTracer (pt/reference_path_tracer.{hpp,cpp}) and of the CPU callers of
+// nlrs::rayIntersectBvh (bvh-visualizer/main.cpp:60-78, pt/main.cpp:214-218).
+//
+// Compiled by nvcc for sm_100a only, with -fmad=false (see rf_vec.h).  There is no CPU fallback:
+// every entry point fails with RF_ERROR_CUDA when no device is usable.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <vector>
+
+using namespace rfb200;
+
+namespace
+{
+#define RF_CUDA(expr)                                                                               \
+    do                                                                                              \
+    {                                                                                               \
+        const cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess)                                                                   \
+        {                                                                                           \
+            return setError(RF_ERROR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+        }                                                                                           \
+    } while (0)
+
+template<typename T>
+struct DeviceBuffer
+{
+    T*          ptr = nullptr;
+    std::size_t count = 0;
+
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer() { release(); }
+
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr, count = 0;
+    }
+    cudaError_t allocate(std::size_t n)
+    {
+        release();
+        if (n == 0) n = 1;
+        const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T));
+        if (e == cudaSuccess) count = n;
+        return e;
+    }
+};
+
+rf_status selectDevice(int32_t device, int& outDevice, int& numSms)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    {
+        cudaGetLastError();
+        return setError(RF_ERROR_CUDA, "No CUDA device available: the rayfinder_b200 render path has no CPU fallback.");
+    }
+    if (device < 0)
+    {
+        RF_CUDA(cudaGetDevice(&outDevice));
+    }
+    else
+    {
+        if (device >= n) return setError(RF_ERROR_INVALID_ARGUMENT, "CUDA device %d out of range (%d devices).", device, n);
+        outDevice = device;
+    }
+    RF_CUDA(cudaSetDevice(outDevice));
+    RF_CUDA(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, outDevice));
+    return RF_OK;
+}
+
+// Structural validation of a BVH before it is handed to the kernels: child indices strictly
+// increase along any descent (=> termination), leaf ranges lie inside the triangle array, interior
+// split axes are 0..2, and the deepest leaf fits the reference's 32-entry stack
+// (ray_intersection.cpp:148,194; wgsl:327,375).
+rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uint64_t numTriangles)
+{
+    if (numNodes == 0 || numNodes >= 0x7FFFFFFFull) return setError(RF_ERROR_INVALID_ARGUMENT, "BVH must have between 1 and 2^31-1 nodes.");
+    if (numTriangles >= (1ull << 30)) return setError(RF_ERROR_INVALID_ARGUMENT, "Too many triangles.");
+    for (std::uint64_t i = 0; i < numNodes; ++i)
+    {
+        const rf_bvh_node& n = nodes[i];
+        if (n.triangle_count > 0)
+        {
+            if (static_cast<std::uint64_t>(n.triangles_offset) + n.triangle_count > numTriangles)
+                return setError(RF_ERROR_INVALID_ARGUMENT, "BVH leaf %llu references triangles out of range.", (unsigned long long)i);
+            if (n.triangle_count >= (1u << 30))
+                return setError(RF_ERROR_INVALID_ARGUMENT, "BVH leaf %llu has too many triangles.", (unsigned long long)i);
+        }
+        else
+        {
+            if (n.split_axis > 2u) return setError(RF_ERROR_INVALID_ARGUMENT, "BVH interior node %llu has split axis %u.", (unsigned long long)i, n.split_axis);
+            if (i + 1 >= numNodes || n.second_child_offset <= i + 1 || n.second_child_offset >= numNodes)
+                return setError(RF_ERROR_INVALID_ARGUMENT, "BVH interior node %llu has child indices out of order.", (unsigned long long)i);
+        }
+    }
+    // Depth check (explicit stack; the tree is a proper pre-order tree after the checks above).
+    std::vector<std::pair<std::uint32_t, std::uint32_t>> stack;
+    stack.emplace_back(0u, 0u);
+    std::uint32_t maxPending = 0;
+    while (!stack.empty())
+    {
+        auto [idx, pending] = stack.back();
+        stack.pop_back();
+        const rf_bvh_node& n = nodes[idx];
+        if (n.triangle_count == 0)
+        {
+            // descending into one child leaves the other pending on the traversal stack
+            maxPending = std::max(maxPending, pending + 1);
+            stack.emplace_back(idx + 1, pending + 1);
+            stack.emplace_back(n.second_child_offset, pending + 1);
+        }
+    }
+    if (maxPending > static_cast<std::uint32_t>(RF_STACK_SIZE))
+        return setError(RF_ERROR_INVALID_ARGUMENT, "BVH depth %u exceeds the traversal stack of %d entries.", maxPending, RF_STACK_SIZE);
+    return RF_OK;
+}
+
+bool sameParams(const rf_render_parameters& a, const rf_render_parameters& b)
+{
+    // RenderParameters::operator== (reference_path_tracer.hpp:42): member-wise, floats by value.
+    const auto eq3 = [](const float* x, const float* y) { return x[0] == y[0] && x[1] == y[1] && x[2] == y[2]; };
+    return a.framebuffer_width == b.framebuffer_width && a.framebuffer_height == b.framebuffer_height &&
+           eq3(a.camera.origin, b.camera.origin) && eq3(a.camera.lower_left_corner, b.camera.lower_left_corner) &&
+           eq3(a.camera.horizontal, b.camera.horizontal) && eq3(a.camera.vertical, b.camera.vertical) &&
+           eq3(a.camera.up, b.camera.up) && eq3(a.camera.right, b.camera.right) &&
+           a.camera.lens_radius == b.camera.lens_radius &&
+           a.sampling_params.num_samples_per_pixel == b.sampling_params.num_samples_per_pixel &&
+           a.sampling_params.num_bounces == b.sampling_params.num_bounces && a.sky.turbidity == b.sky.turbidity &&
+           eq3(a.sky.albedo, b.sky.albedo) && a.sky.sun_zenith_degrees == b.sky.sun_zenith_degrees &&
+           a.sky.sun_azimuth_degrees == b.sky.sun_azimuth_degrees && a.exposure == b.exposure;
+}
+
+rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std::uint32_t maxH)
+{
+    if (p.framebuffer_width == 0 || p.framebuffer_height == 0 || p.framebuffer_width > maxW || p.framebuffer_height > maxH)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "Framebuffer size %ux%u outside (0, %ux%u].", p.framebuffer_width, p.framebuffer_height, maxW, maxH);
+    if (p.sampling_params.num_samples_per_pixel == 0 || p.sampling_params.num_samples_per_pixel > 65536u)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "numSamplesPerPixel must be in [1, 65536].");
+    if (p.sampling_params.num_bounces == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "numBounces must be >= 1.");
+    return RF_OK;
+}
+} // namespace
+
+// =================================================================================================
+struct rf_renderer
+{
+    int          device = 0;
+    int          numSms = 0;
+    cudaStream_t stream = nullptr; // default stream unless rf_renderer_set_stream is called
+
+    // scene
+    DeviceBuffer<float4>        nodes, tris, vattr;
+    DeviceBuffer<uint4>         texDesc;
+    DeviceBuffer<std::uint32_t> texels;
+    DeviceBuffer<uchar2>        blueNoise;
+    DeviceBuffer<SampleLutRow>  lut;
+    DeviceBuffer<float>         srgbLut;
+    std::uint32_t               numTextures = 0;
+    std::uint64_t               numTexels = 0;
+
+    // frame state
+    std::uint32_t               maxW = 0, maxH = 0;
+    DeviceBuffer<float4>        image, radiance;
+    DeviceBuffer<float4>        queueMem; // 2 queues x 4 arrays
+    DeviceBuffer<HitRecord>     hits;
+    DeviceBuffer<std::uint32_t> ownedTiles;
+    DeviceBuffer<FrameCounters> counters;
+    DeviceBuffer<unsigned long long> stats;
+    DeviceBuffer<std::uint32_t> display;
+    PathQueue                   queues[2]{};
+    std::uint64_t               maxPaths = 0;
+
+    rf_render_parameters params{};
+    rf_sky_state         skyState{};
+    std::uint32_t        lutRows = 0;
+    std::uint32_t        frameCount = 0;
+    std::uint32_t        accumulated = 0;
+    std::uint32_t        rank = 0, world = 1;
+    std::uint32_t        numOwnedTiles = 0, tilesX = 0;
+    bool                 tilesDirty = true;
+
+    // timing
+    struct Timed
+    {
+        cudaEvent_t begin, end;
+    };
+    std::vector<Timed>  eventPool;
+    std::deque<Timed>   pending;
+    std::deque<float>   durationsMs; // last <= 30 completed passes
+    double              totalMs = 0.0;
+    std::uint64_t       frames = 0;
+    bool                stageTiming = false;
+    std::vector<cudaEvent_t> stageEvents;
+    double              msClosest = 0, msShadow = 0, msShade = 0, msOther = 0;
+
+    ~rf_renderer()
+    {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        for (auto& t : eventPool)
+        {
+            cudaEventDestroy(t.begin);
+            cudaEventDestroy(t.end);
+        }
+        for (auto& t : pending)
+        {
+            cudaEventDestroy(t.begin);
+            cudaEventDestroy(t.end);
+        }
+        for (auto e : stageEvents) cudaEventDestroy(e);
+    }
+
+    void drainTimings(bool wait)
+    {
+        while (!pending.empty())
+        {
+            Timed t = pending.front();
+            if (wait)
+            {
+                cudaEventSynchronize(t.end);
+            }
+            else if (cudaEventQuery(t.end) != cudaSuccess)
+            {
+                cudaGetLastError();
+                break;
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t.begin, t.end);
+            durationsMs.push_back(ms);
+            if (durationsMs.size() > 30) durationsMs.pop_front(); // reference_path_tracer.cpp:689-693
+            totalMs += ms;
+            pending.pop_front();
+            eventPool.push_back(t);
+        }
+    }
+
+    rf_status applyParams(const rf_render_parameters& p)
+    {
+        params = p;
+        accumulated = 0; // reset the temporal accumulation (reference_path_tracer.cpp:561)
+        tilesDirty = true;
+        const rf_status st = rf_sky_state_new(&p.sky, &skyState);
+        if (st != RF_OK) return st;
+        // Sampling tables for every n = frameCount % numSamplesPerPixel.
+        const std::uint32_t spp = p.sampling_params.num_samples_per_pixel;
+        if (spp != lutRows)
+        {
+            std::vector<SampleLutRow> rows(spp);
+            for (std::uint32_t n = 0; n < spp; ++n) buildSampleLutRow(n, rows[n]);
+            RF_CUDA(cudaStreamSynchronize(stream));
+            RF_CUDA(lut.allocate(spp));
+            RF_CUDA(cudaMemcpy(lut.ptr, rows.data(), spp * sizeof(SampleLutRow), cudaMemcpyHostToDevice));
+            lutRows = spp;
+        }
+        return RF_OK;
+    }
+
+    rf_status updateTiles()
+    {
+        if (!tilesDirty) return RF_OK;
+        tilesX = (params.framebuffer_width + TILE - 1) / TILE;
+        const std::uint32_t tilesY = (params.framebuffer_height + TILE - 1) / TILE;
+        std::vector<std::uint32_t> owned;
+        for (std::uint32_t ty = 0; ty < tilesY; ++ty)
+            for (std::uint32_t tx = 0; tx < tilesX; ++tx)
+                if ((tx + ty) % world == rank) owned.push_back(ty * tilesX + tx);
+        numOwnedTiles = static_cast<std::uint32_t>(owned.size());
+        RF_CUDA(cudaStreamSynchronize(stream));
+        if (!owned.empty())
+            RF_CUDA(cudaMemcpy(ownedTiles.ptr, owned.data(), owned.size() * sizeof(std::uint32_t), cudaMemcpyHostToDevice));
+        tilesDirty = false;
+        return RF_OK;
+    }
+
+    int gridFor(int blocksPerSm) const { return numSms * blocksPerSm; }
+};
+
+extern "C" rf_status rf_renderer_create(
+    const rf_renderer_descriptor* desc,
+    const rf_scene*               scene,
+    const int32_t                 device,
+    rf_renderer**                 out)
+{
+    if (!desc || !scene || !out) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_create: null argument");
+    if (desc->max_framebuffer_width <= 0 || desc->max_framebuffer_height <= 0)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "maxFramebufferSize must be positive.");
+    if (!scene->bvh_nodes || !scene->position_attributes || !scene->vertex_attributes || !scene->base_color_textures ||
+        scene->num_base_color_textures == 0)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "Scene spans must be non-empty.");
+    if (scene->num_position_attributes != scene->num_vertex_attributes)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "positionAttributes and vertexAttributes must have the same length.");
+    rf_status st = validateBvh(scene->bvh_nodes, scene->num_bvh_nodes, scene->num_position_attributes);
+    if (st != RF_OK) return st;
+    st = validateParams(desc->render_params, desc->max_framebuffer_width, desc->max_framebuffer_height);
+    if (st != RF_OK) return st;
+
+    auto r = std::make_unique<rf_renderer>();
+    st = selectDevice(device, r->device, r->numSms);
+    if (st != RF_OK) return st;
+
+    // Texture descriptors + concatenated texels (reference_path_tracer.cpp:209-270).
+    std::vector<uint4> descs;
+    std::uint64_t      totalTexels = 0;
+    for (std::uint64_t i = 0; i < scene->num_base_color_textures; ++i)
+    {
+        const rf_texture& t = scene->base_color_textures[i];
+        if (!t.pixels || t.width == 0 || t.height == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "Texture %llu is empty.", (unsigned long long)i);
+        descs.push_back(make_uint4(t.width, t.height, static_cast<std::uint32_t>(totalTexels), 0u));
+        totalTexels += static_cast<std::uint64_t>(t.width) * t.height;
+    }
+    const std::uint64_t textureBytes = totalTexels * 4;
+    const std::uint64_t maxBinding = 1ull << 30; // REQUIRED_LIMITS.maxStorageBufferBindingSize, pt/gpu_limits.hpp:20-25
+    if (textureBytes > maxBinding)
+        return setError(
+            RF_ERROR_INVALID_ARGUMENT,
+            "Texture buffer size (%llu) exceeds maxStorageBufferBindingSize (%llu).",
+            (unsigned long long)textureBytes,
+            (unsigned long long)maxBinding);
+
+    const std::uint64_t numNodes = scene->num_bvh_nodes, numTris = scene->num_position_attributes;
+    {
+        // Upload in the reference layouts, then repack on the device.
+        DeviceBuffer<rf_bvh_node> rawNodes;
+        DeviceBuffer<float>       rawTris;
+        RF_CUDA(rawNodes.allocate(numNodes));
+        RF_CUDA(rawTris.allocate(numTris * 12));
+        RF_CUDA(cudaMemcpy(rawNodes.ptr, scene->bvh_nodes, numNodes * sizeof(rf_bvh_node), cudaMemcpyHostToDevice));
+        RF_CUDA(cudaMemcpy(rawTris.ptr, scene->position_attributes, numTris * sizeof(rf_position_attribute), cudaMemcpyHostToDevice));
+        RF_CUDA(r->nodes.allocate(2 * numNodes));
+        RF_CUDA(r->tris.allocate(3 * numTris));
+        k_pack_nodes<<<r->numSms * 4, 256>>>(rawNodes.ptr, numNodes, r->nodes.ptr);
+        k_pack_triangles<<<r->numSms * 4, 256>>>(rawTris.ptr, 4, numTris, r->tris.ptr);
+        RF_CUDA(cudaGetLastError());
+        RF_CUDA(cudaDeviceSynchronize());
+    }
+    RF_CUDA(r->vattr.allocate(5 * numTris));
+    RF_CUDA(cudaMemcpy(r->vattr.ptr, scene->vertex_attributes, numTris * sizeof(rf_vertex_attributes), cudaMemcpyHostToDevice));
+    RF_CUDA(r->texDesc.allocate(descs.size()));
+    RF_CUDA(cudaMemcpy(r->texDesc.ptr, descs.data(), descs.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    RF_CUDA(r->texels.allocate(totalTexels));
+    for (std::uint64_t i = 0; i < scene->num_base_color_textures; ++i)
+    {
+        const rf_texture& t = scene->base_color_textures[i];
+        RF_CUDA(cudaMemcpy(r->texels.ptr + descs[i].z, t.pixels, static_cast<std::uint64_t>(t.width) * t.height * 4, cudaMemcpyHostToDevice));
+    }
+    r->numTextures = static_cast<std::uint32_t>(descs.size());
+    r->numTexels = totalTexels;
+
+    RF_CUDA(r->blueNoise.allocate(BLUE_NOISE_WIDTH * BLUE_NOISE_HEIGHT));
+    RF_CUDA(cudaMemcpy(r->blueNoise.ptr, rf_blue_noise_rg8, BLUE_NOISE_WIDTH * BLUE_NOISE_HEIGHT * 2, cudaMemcpyHostToDevice));
+    float srgb[256];
+    buildSrgbLut(srgb);
+    RF_CUDA(r->srgbLut.allocate(256));
+    RF_CUDA(cudaMemcpy(r->srgbLut.ptr, srgb, sizeof(srgb), cudaMemcpyHostToDevice));
+
+    // Frame buffers sized for maxFramebufferSize (reference_path_tracer.cpp:186-190).
+    r->maxW = static_cast<std::uint32_t>(desc->max_framebuffer_width);
+    r->maxH = static_cast<std::uint32_t>(desc->max_framebuffer_height);
+    const std::uint64_t maxPixels = static_cast<std::uint64_t>(r->maxW) * r->maxH;
+    const std::uint64_t maxTiles = static_cast<std::uint64_t>((r->maxW + TILE - 1) / TILE) * ((r->maxH + TILE - 1) / TILE);
+    r->maxPaths = maxPixels;
+    RF_CUDA(r->image.allocate(maxPixels));
+    RF_CUDA(r->radiance.allocate(maxPixels));
+    RF_CUDA(r->display.allocate(maxPixels));
+    RF_CUDA(r->hits.allocate(maxPixels));
+    RF_CUDA(r->queueMem.allocate(maxPixels * 8));
+    RF_CUDA(r->ownedTiles.allocate(maxTiles));
+    RF_CUDA(r->counters.allocate(1));
+    RF_CUDA(r->stats.allocate(STAT_COUNT));
+    RF_CUDA(cudaMemset(r->image.ptr, 0, maxPixels * sizeof(float4)));
+    RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
+    for (int q = 0; q < 2; ++q)
+    {
+        float4* base = r->queueMem.ptr + static_cast<std::uint64_t>(q) * 4 * maxPixels;
+        r->queues[q] = PathQueue{base, base + maxPixels, base + 2 * maxPixels, base + 3 * maxPixels};
+    }
+
+    st = r->applyParams(desc->render_params);
+    if (st != RF_OK) return st;
+    *out = r.release();
+    return RF_OK;
+}
+
+extern "C" void rf_renderer_destroy(rf_renderer* r) { delete r; }
+
+extern "C" rf_status rf_renderer_set_render_parameters(rf_renderer* r, const rf_render_parameters* params)
+{
+    if (!r || !params) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_render_parameters: null argument");
+    if (sameParams(r->params, *params)) return RF_OK; // reference_path_tracer.cpp:558
+    const rf_status st = validateParams(*params, r->maxW, r->maxH);
+    if (st != RF_OK) return st;
+    RF_CUDA(cudaSetDevice(r->device));
+    return r->applyParams(*params);
+}
+
+extern "C" rf_status rf_renderer_set_tile_partition(rf_renderer* r, std::uint32_t rank, std::uint32_t world)
+{
+    if (!r || world == 0 || rank >= world) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tile_partition: need rank < world, world >= 1");
+    r->rank = rank, r->world = world;
+    r->tilesDirty = true;
+    r->accumulated = 0;
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_render(rf_renderer* r)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_render: null renderer");
+    RF_CUDA(cudaSetDevice(r->device));
+    const std::uint32_t spp = r->params.sampling_params.num_samples_per_pixel;
+    const std::uint32_t frameCount = r->frameCount++; // mFrameCount++ (reference_path_tracer.cpp:580)
+    if (r->accumulated >= spp) return RF_OK;          // fsMain:51 — nothing is traced once converged
+
+    rf_status st = r->updateTiles();
+    if (st != RF_OK) return st;
+    r->drainTimings(false);
+
+    cudaStream_t s = r->stream;
+    FrameParams  fp{};
+    fp.width = r->params.framebuffer_width;
+    fp.height = r->params.framebuffer_height;
+    fp.frameCount = frameCount;
+    fp.sampleIndex = frameCount % spp;
+    fp.numBounces = r->params.sampling_params.num_bounces;
+    fp.numOwnedTiles = r->numOwnedTiles;
+    fp.tilesX = r->tilesX;
+    fp.numTextures = r->numTextures;
+    fp.numTexels = r->numTexels;
+    fp.camera = r->params.camera;
+    fp.sky = r->skyState;
+    const SolarConstants sc = solarConstants();
+    fp.solarCosThetaMax = sc.cosThetaMax;
+    fp.solarInvPdf = sc.invPdf;
+
+    SceneDevice scene{r->nodes.ptr, r->tris.ptr, r->vattr.ptr, r->texDesc.ptr, r->texels.ptr, r->blueNoise.ptr, r->lut.ptr, r->srgbLut.ptr};
+
+    rf_renderer::Timed t{};
+    if (!r->eventPool.empty())
+    {
+        t = r->eventPool.back();
+        r->eventPool.pop_back();
+    }
+    else
+    {
+        RF_CUDA(cudaEventCreate(&t.begin));
+        RF_CUDA(cudaEventCreate(&t.end));
+    }
+    std::size_t stageIdx = 0;
+    const auto  stageMark = [&]() -> cudaError_t {
+        if (!r->stageTiming) return cudaSuccess;
+        if (stageIdx >= r->stageEvents.size())
+        {
+            cudaEvent_t e;
+            const cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            r->stageEvents.push_back(e);
+        }
+        return cudaEventRecord(r->stageEvents[stageIdx++], s);
+    };
+
+    RF_CUDA(cudaEventRecord(t.begin, s));
+    const std::uint64_t numPixels = static_cast<std::uint64_t>(fp.width) * fp.height;
+    if (r->accumulated == 0)
+    {
+        // fsMain:45-47: imageBuffer[idx] = vec3(0f) on the first sample (also clears non-owned tiles).
+        RF_CUDA(cudaMemsetAsync(r->image.ptr, 0, numPixels * sizeof(float4), s));
+    }
+    FrameCounters* ctr = r->counters.ptr;
+    RF_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
+
+    const int gridLight = r->gridFor(8);
+    const int gridTrace = r->gridFor(6);
+    RF_CUDA(stageMark());
+    if (fp.numOwnedTiles > 0)
+    {
+        k_raygen<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->ownedTiles.ptr, r->queues[0], ctr, r->radiance.ptr, r->stats.ptr);
+        RF_CUDA(stageMark());
+        for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
+        {
+            const int      in = (bounce - 1) & 1, outQ = bounce & 1;
+            std::uint32_t* inCount = &ctr->queueCount[in];
+            std::uint32_t* outCount = &ctr->queueCount[outQ];
+            RF_CUDA(cudaMemsetAsync(outCount, 0, sizeof(std::uint32_t) + 0, s));
+            RF_CUDA(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(ctr->fetch), s));
+            k_closest<<<gridTrace, BLOCK_THREADS, 0, s>>>(scene, r->queues[in], inCount, &ctr->fetch[0], r->hits.ptr, r->stats.ptr);
+            RF_CUDA(stageMark());
+            k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], inCount, r->hits.ptr, r->queues[outQ], outCount, r->radiance.ptr);
+            RF_CUDA(stageMark());
+            k_shadow<<<gridTrace, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[outQ], outCount, &ctr->fetch[2], r->radiance.ptr, r->stats.ptr);
+            RF_CUDA(stageMark());
+        }
+        k_accumulate<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, r->ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+    }
+    RF_CUDA(stageMark());
+    RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaEventRecord(t.end, s));
+    r->pending.push_back(t);
+    r->frames++;
+    r->accumulated = std::min(r->accumulated + 1, spp); // reference_path_tracer.cpp:590-591
+
+    if (r->stageTiming)
+    {
+        RF_CUDA(cudaStreamSynchronize(s));
+        // events: [0]=before raygen, [1]=after raygen, then per bounce 3, then final
+        float ms = 0.f;
+        std::size_t e = 0;
+        if (fp.numOwnedTiles > 0)
+        {
+            cudaEventElapsedTime(&ms, r->stageEvents[0], r->stageEvents[1]);
+            r->msOther += ms;
+            e = 1;
+            for (std::uint32_t b = 0; b < fp.numBounces; ++b)
+            {
+                cudaEventElapsedTime(&ms, r->stageEvents[e], r->stageEvents[e + 1]);
+                r->msClosest += ms;
+                cudaEventElapsedTime(&ms, r->stageEvents[e + 1], r->stageEvents[e + 2]);
+                r->msShade += ms;
+                cudaEventElapsedTime(&ms, r->stageEvents[e + 2], r->stageEvents[e + 3]);
+                r->msShadow += ms;
+                e += 3;
+            }
+            cudaEventElapsedTime(&ms, r->stageEvents[e], r->stageEvents[e + 1]);
+            r->msOther += ms;
+        }
+    }
+    return RF_OK;
+}
+
+extern "C" float rf_renderer_average_renderpass_duration_ms(rf_renderer* r)
+{
+    if (!r) return 0.0f;
+    cudaSetDevice(r->device);
+    r->drainTimings(false);
+    if (r->durationsMs.empty()) return 0.0f; // reference_path_tracer.cpp:708-711
+    double sum = 0.0;
+    for (float ms : r->durationsMs) sum += ms;
+    return static_cast<float>(sum / static_cast<double>(r->durationsMs.size()));
+}
+
+extern "C" float rf_renderer_render_progress_percentage(const rf_renderer* r)
+{
+    if (!r) return 0.0f;
+    return 100.0f * static_cast<float>(r->accumulated) / static_cast<float>(r->params.sampling_params.num_samples_per_pixel);
+}
+
+extern "C" rf_status rf_renderer_read_hdr(rf_renderer* r, float* dst, std::uint64_t numFloats, std::uint32_t* accumulated)
+{
+    if (!r || !dst) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_hdr: null argument");
+    const std::uint64_t need = static_cast<std::uint64_t>(r->params.framebuffer_width) * r->params.framebuffer_height * 4;
+    if (numFloats < need) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_hdr: need %llu floats, got %llu", (unsigned long long)need, (unsigned long long)numFloats);
+    RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaMemcpyAsync(dst, r->image.ptr, need * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    if (accumulated) *accumulated = r->accumulated;
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_read_display(rf_renderer* r, std::uint32_t* dst, std::uint64_t numPixels)
+{
+    if (!r || !dst) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_display: null argument");
+    const std::uint64_t need = static_cast<std::uint64_t>(r->params.framebuffer_width) * r->params.framebuffer_height;
+    if (numPixels < need) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_display: need %llu pixels", (unsigned long long)need);
+    RF_CUDA(cudaSetDevice(r->device));
+    const float acc = static_cast<float>(std::max(r->accumulated, 1u));
+    k_display<<<r->gridFor(8), BLOCK_THREADS, 0, r->stream>>>(static_cast<std::uint32_t>(need), r->image.ptr, acc, r->params.exposure, r->display.ptr);
+    RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaMemcpyAsync(dst, r->display.ptr, need * 4, cudaMemcpyDeviceToHost, r->stream));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    return RF_OK;
+}
+
+extern "C" void* rf_renderer_hdr_device_ptr(rf_renderer* r) { return r ? r->image.ptr : nullptr; }
+
+extern "C" rf_status rf_renderer_set_stream(rf_renderer* r, void* cudaStream)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_stream: null renderer");
+    RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    r->stream = static_cast<cudaStream_t>(cudaStream);
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_synchronize(rf_renderer* r)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_synchronize: null renderer");
+    RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    r->drainTimings(true);
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_set_frame_count(rf_renderer* r, std::uint32_t frameCount)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_frame_count: null renderer");
+    r->frameCount = frameCount;
+    return RF_OK;
+}
+extern "C" std::uint32_t rf_renderer_frame_count(const rf_renderer* r) { return r ? r->frameCount : 0; }
+extern "C" std::uint32_t rf_renderer_accumulated_sample_count(const rf_renderer* r) { return r ? r->accumulated : 0; }
+
+extern "C" rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out)
+{
+    if (!r || !out) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_get_stats: null argument");
+    RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    r->drainTimings(true);
+    unsigned long long s[STAT_COUNT];
+    RF_CUDA(cudaMemcpy(s, r->stats.ptr, sizeof(s), cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof(*out));
+    out->frames = r->frames;
+    out->paths = s[STAT_PATHS];
+    out->closest_rays = s[STAT_CLOSEST_RAYS];
+    out->shadow_rays = s[STAT_SHADOW_RAYS];
+    out->closest_nodes_visited = s[STAT_CLOSEST_NODES];
+    out->closest_triangles_tested = s[STAT_CLOSEST_TRIS];
+    out->shadow_nodes_visited = s[STAT_SHADOW_NODES];
+    out->shadow_triangles_tested = s[STAT_SHADOW_TRIS];
+    out->device_ms_total = r->totalMs;
+    out->device_ms_closest = r->msClosest;
+    out->device_ms_shadow = r->msShadow;
+    out->device_ms_shade = r->msShade;
+    out->device_ms_other = r->msOther;
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_reset_stats(rf_renderer* r)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_reset_stats: null renderer");
+    RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    r->drainTimings(true);
+    RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
+    r->frames = 0;
+    r->totalMs = r->msClosest = r->msShadow = r->msShade = r->msOther = 0.0;
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_stage_timing: null renderer");
+    r->stageTiming = enabled != 0;
+    return RF_OK;
+}
+
+// =================================================================================================
+struct rf_traversal_scene
+{
+    int                  device = 0;
+    int                  numSms = 0;
+    DeviceBuffer<float4> nodes, tris;
+    std::uint64_t        numNodes = 0, numTris = 0;
+};
+
+extern "C" rf_status rf_traversal_scene_create(
+    const rf_bvh_node*   nodes,
+    std::uint64_t        numNodes,
+    const rf_positions*  triangles,
+    std::uint64_t        numTriangles,
+    int32_t              device,
+    rf_traversal_scene** out)
+{
+    if (!nodes || !triangles || !out || numTriangles == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_traversal_scene_create: null or empty argument");
+    rf_status st = validateBvh(nodes, numNodes, numTriangles);
+    if (st != RF_OK) return st;
+    auto s = std::make_unique<rf_traversal_scene>();
+    st = selectDevice(device, s->device, s->numSms);
+    if (st != RF_OK) return st;
+    DeviceBuffer<rf_bvh_node> rawNodes;
+    DeviceBuffer<float>       rawTris;
+    RF_CUDA(rawNodes.allocate(numNodes));
+    RF_CUDA(rawTris.allocate(numTriangles * 9));
+    RF_CUDA(cudaMemcpy(rawNodes.ptr, nodes, numNodes * sizeof(rf_bvh_node), cudaMemcpyHostToDevice));
+    RF_CUDA(cudaMemcpy(rawTris.ptr, triangles, numTriangles * sizeof(rf_positions), cudaMemcpyHostToDevice));
+    RF_CUDA(s->nodes.allocate(2 * numNodes));
+    RF_CUDA(s->tris.allocate(3 * numTriangles));
+    k_pack_nodes<<<s->numSms * 4, 256>>>(rawNodes.ptr, numNodes, s->nodes.ptr);
+    k_pack_triangles<<<s->numSms * 4, 256>>>(rawTris.ptr, 3, numTriangles, s->tris.ptr);
+    RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaDeviceSynchronize());
+    s->numNodes = numNodes, s->numTris = numTriangles;
+    *out = s.release();
+    return RF_OK;
+}
+
+extern "C" void rf_traversal_scene_destroy(rf_traversal_scene* s)
+{
+    if (s) cudaSetDevice(s->device);
+    delete s;
+}
+
+extern "C" rf_status rf_ray_intersect_bvh(
+    rf_traversal_scene* s,
+    const float*        rays,
+    std::uint64_t       numRays,
+    float               rayTMax,
+    std::uint8_t*       outHit,
+    float*              outPT,
+    std::uint32_t*      outNodes)
+{
+    if (!s || (!rays && numRays)) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_ray_intersect_bvh: null argument");
+    if (numRays == 0) return RF_OK;
+    RF_CUDA(cudaSetDevice(s->device));
+    DeviceBuffer<float>         dRays;
+    DeviceBuffer<std::uint8_t>  dHit;
+    DeviceBuffer<float4>        dPT;
+    DeviceBuffer<std::uint32_t> dNodes;
+    RF_CUDA(dRays.allocate(numRays * 6));
+    RF_CUDA(cudaMemcpy(dRays.ptr, rays, numRays * 6 * sizeof(float), cudaMemcpyHostToDevice));
+    if (outHit) RF_CUDA(dHit.allocate(numRays));
+    if (outPT) RF_CUDA(dPT.allocate(numRays));
+    if (outNodes) RF_CUDA(dNodes.allocate(numRays));
+    const std::uint64_t blocksNeeded = (numRays + BLOCK_THREADS - 1) / BLOCK_THREADS;
+    const int           grid = static_cast<int>(std::min<std::uint64_t>(blocksNeeded, static_cast<std::uint64_t>(s->numSms) * 8));
+    k_intersect_batch<<<grid, BLOCK_THREADS>>>(s->nodes.ptr, s->tris.ptr, dRays.ptr, numRays, rayTMax, dHit.ptr, dPT.ptr, dNodes.ptr);
+    RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaDeviceSynchronize());
+    if (outHit) RF_CUDA(cudaMemcpy(outHit, dHit.ptr, numRays, cudaMemcpyDeviceToHost));
+    if (outPT) RF_CUDA(cudaMemcpy(outPT, dPT.ptr, numRays * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (outNodes) RF_CUDA(cudaMemcpy(outNodes, dNodes.ptr, numRays * sizeof(std::uint32_t), cudaMemcpyDeviceToHost));
+    return RF_OK;
+}
+
+extern "C" rf_status rf_bvh_visualizer_node_counts(
+    rf_traversal_scene* s,
+    const rf_camera*    camera,
+    std::uint32_t       width,
+    std::uint32_t       height,
+    float               rayTMax,
+    std::uint32_t*      outNodes,
+    float*              deviceMs)
+{
+    if (!s || !camera || !outNodes || width == 0 || height == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_bvh_visualizer_node_counts: bad argument");
+    RF_CUDA(cudaSetDevice(s->device));
+    const std::uint64_t         numPixels = static_cast<std::uint64_t>(width) * height;
+    DeviceBuffer<std::uint32_t> dNodes;
+    RF_CUDA(dNodes.allocate(numPixels));
+    cudaEvent_t e0, e1;
+    RF_CUDA(cudaEventCreate(&e0));
+    RF_CUDA(cudaEventCreate(&e1));
+    RF_CUDA(cudaEventRecord(e0));
+    k_visualizer<<<s->numSms * 8, BLOCK_THREADS>>>(s->nodes.ptr, s->tris.ptr, *camera, width, height, rayTMax, dNodes.ptr);
+    RF_CUDA(cudaEventRecord(e1));
+    RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaDeviceSynchronize());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (deviceMs) *deviceMs = ms;
+    RF_CUDA(cudaMemcpy(outNodes, dNodes.ptr, numPixels * sizeof(std::uint32_t), cudaMemcpyDeviceToHost));
+    return RF_OK;
+}
+
+extern "C" int32_t     rf_has_cuda_kernels(void) { return 1; }
+#define RF_STR2(x) #x
+#define RF_STR(x) RF_STR2(x)
+extern "C" const char* rf_build_info(void) { return "rayfinder_b200 sm_100a -fmad=false cudart " RF_STR(CUDART_VERSION); }

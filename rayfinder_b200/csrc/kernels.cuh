@@ -1,0 +1,548 @@
+// Wavefront stages of the B200 render path.  Each kernel restates one part of the reference's
+// single fragment shader (pt/reference_path_tracer.wgsl); see DESIGN.md for the stage graph.
+//
+//   k_raygen      fsMain:34-55 (pixel mapping, animatedBlueNoise:603-616, generateCameraRay:237-245)
+//   k_closest     rayIntersectBvh:371-429 for every live path (persistent warps, dynamic fetch)
+//   k_shade       rayColor:181-234 minus the two traversals: hit attributes (:393-400), evalTexture
+//                 (:304-307,553-565), sun sample (:288-292), Lambert scatter (:295-301), sky on miss
+//                 (:213-227,248-275); appends surviving paths to the next queue (stream compaction)
+//   k_shadow      shadowRay:323-368 + the NEE accumulation of rayColor:203
+//   k_accumulate  imageBuffer[idx] += rayColor(...) (fsMain:55)
+//   k_display     estimator / acesFilmic / gamma (fsMain:59-63, :278-285)
+#pragma once
+
+#include "rf_internal.h"
+#include "traversal.cuh"
+
+namespace rfb200
+{
+constexpr int TILE = 32;           // ownership tile edge (pixels)
+constexpr int TILE_PIXELS = 1024;  // TILE * TILE
+constexpr int BLOCK_THREADS = 256;
+
+// One queue of live paths (structure of float4 arrays; entry i of each array belongs to path i).
+struct PathQueue
+{
+    float4* originPix;   // ray origin xyz, w = pixel index (bits)
+    float4* direction;   // ray direction xyz (not normalised after the first bounce, as in the reference)
+    float4* throughput;  // path throughput xyz
+    float4* contribution; // throughput * lightIntensity * reflectance of the hit that spawned the entry
+};
+
+// Uniform block: RenderParamsLayout (reference_path_tracer.cpp:35-120) + AlignedSkyState + constants.
+struct FrameParams
+{
+    std::uint32_t width, height;
+    std::uint32_t frameCount;
+    std::uint32_t sampleIndex; // frameCount % numSamplesPerPixel
+    std::uint32_t numBounces;
+    std::uint32_t numOwnedTiles;
+    std::uint32_t tilesX;
+    std::uint32_t numTextures;
+    std::uint64_t numTexels;
+    rf_camera     camera;
+    rf_sky_state  sky;
+    float         solarCosThetaMax;
+    float         solarInvPdf;
+};
+
+struct SceneDevice
+{
+    const float4*        nodes;      // 2 x float4 per node
+    const float4*        tris;       // 3 x float4 per triangle
+    const float4*        vattr;      // 5 x float4 per triangle (VertexAttributes as-is)
+    const uint4*         texDesc;    // (width, height, offset, 0)
+    const std::uint32_t* texels;     // BGRA8
+    const uchar2*        blueNoise;  // 128 x 128
+    const SampleLutRow*  lut;        // one row per sample index
+    const float*         srgbLut;    // 256
+};
+
+// Device counters, zeroed at the start of every frame.
+struct FrameCounters
+{
+    std::uint32_t queueCount[2];   // entries in queue A / B (ping-pong)
+    std::uint32_t fetch[4];        // dynamic work-fetch cursors (closest, shade, shadow, spare)
+};
+
+enum StatSlot
+{
+    STAT_PATHS = 0,
+    STAT_CLOSEST_RAYS,
+    STAT_SHADOW_RAYS,
+    STAT_CLOSEST_NODES,
+    STAT_CLOSEST_TRIS,
+    STAT_SHADOW_NODES,
+    STAT_SHADOW_TRIS,
+    STAT_COUNT
+};
+
+__device__ __forceinline__ std::uint32_t laneId() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append: returns the slot for this lane if `pred`, using one atomic per warp.
+__device__ __forceinline__ std::uint32_t warpAppend(std::uint32_t* counter, const bool pred)
+{
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
+    if (mask == 0u) return 0u;
+    const int     leader = __ffs(mask) - 1;
+    std::uint32_t base = 0;
+    if (static_cast<int>(laneId()) == leader) base = atomicAdd(counter, static_cast<std::uint32_t>(__popc(mask)));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + static_cast<std::uint32_t>(__popc(mask & ((1u << laneId()) - 1u)));
+}
+
+__device__ __forceinline__ void warpStatAdd(unsigned long long* stat, std::uint32_t value)
+{
+    const std::uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, value);
+    if (laneId() == 0 && sum != 0u) atomicAdd(stat, static_cast<unsigned long long>(sum));
+}
+
+// WGSL fract(x) = x - floor(x).
+__device__ __forceinline__ float wgslFract(const float x) { return x - floorf(x); }
+
+// pixarOnb (wgsl:310-319) applied to a local vector: mat3x3(u, v, n) * l = l.x*u + l.y*v + l.z*n.
+__device__ __forceinline__ V3 onbTransform(const V3 n, const V3 l)
+{
+    const float s = (n.z >= 0.0f) ? 1.0f : -1.0f;
+    const float a = __fdiv_rn(-1.0f, s + n.z);
+    const float b = n.x * n.y * a;
+    const V3    u = v3(1.0f + s * n.x * n.x * a, s * b, -s * n.x);
+    const V3    v = v3(b, s + n.y * n.y * a, -n.y);
+    return (l.x * u + l.y * v) + l.z * n;
+}
+
+// Path slot -> pixel.  Paths are enumerated tile by tile (32x32 ownership tiles); inside a tile each
+// warp covers an 8x4 pixel block so that the 32 primary rays of a warp are spatially coherent.
+__device__ __forceinline__ bool slotToPixel(
+    const FrameParams& fp,
+    const std::uint32_t* __restrict__ ownedTiles,
+    const std::uint32_t slot,
+    std::uint32_t&      px,
+    std::uint32_t&      py)
+{
+    const std::uint32_t tile = ownedTiles[slot >> 10];
+    const std::uint32_t within = slot & 1023u;
+    const std::uint32_t warp = within >> 5, lane = within & 31u;
+    px = (tile % fp.tilesX) * TILE + (warp & 3u) * 8u + (lane & 7u);
+    py = (tile / fp.tilesX) * TILE + (warp >> 2) * 4u + (lane >> 3);
+    return px < fp.width && py < fp.height;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
+    const FrameParams fp,
+    const SceneDevice scene,
+    const std::uint32_t* __restrict__ ownedTiles,
+    PathQueue           out,
+    FrameCounters*      counters,
+    float4*             radiance,
+    unsigned long long* stats)
+{
+    const std::uint32_t total = fp.numOwnedTiles * TILE_PIXELS;
+    std::uint32_t       generated = 0;
+    for (std::uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < ((total + 31u) & ~31u);
+         slot += gridDim.x * blockDim.x)
+    {
+        std::uint32_t px = 0, py = 0;
+        const bool    valid = slot < total && slotToPixel(fp, ownedTiles, slot, px, py);
+        const std::uint32_t dst = warpAppend(&counters->queueCount[0], valid);
+        if (!valid) continue;
+        ++generated;
+
+        // vsMain/fsMain:10-17,34-43: fragment centre -> texCoord -> coord.
+        const float u = __fdiv_rn(static_cast<float>(px) + 0.5f, static_cast<float>(fp.width));
+        const float v = __fdiv_rn(static_cast<float>(py) + 0.5f, static_cast<float>(fp.height));
+        const std::uint32_t cx = static_cast<std::uint32_t>(u * static_cast<float>(fp.width));
+        const std::uint32_t cy = static_cast<std::uint32_t>(v * static_cast<float>(fp.height));
+        const std::uint32_t idx = cy * fp.width + cx;
+
+        // animatedBlueNoise (tabulated per sample index).
+        const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+        const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+        const float         ux = lut.ux[bn.x], uy = lut.uy[bn.y];
+
+        // jitter = blueNoise / vec2f(dimensions); generateCameraRay(bn, camera, u + j.x, (1 - v) + j.y)
+        const float su = u + __fdiv_rn(ux, static_cast<float>(fp.width));
+        const float sv = (1.0f - v) + __fdiv_rn(uy, static_cast<float>(fp.height));
+
+        // pointInUnitDisk (wgsl:596-600) and the thin lens (wgsl:238-241).
+        const float r = __fsqrt_rn(ux);
+        const float lensX = fp.camera.lens_radius * (r * lut.cosPhi[bn.y]);
+        const float lensY = fp.camera.lens_radius * (r * lut.sinPhi[bn.y]);
+        const V3    lensOffset = lensX * v3(fp.camera.right) + lensY * v3(fp.camera.up);
+        const V3    origin = v3(fp.camera.origin) + lensOffset;
+        const V3    dir = normalize(
+            ((v3(fp.camera.lower_left_corner) + su * v3(fp.camera.horizontal)) + sv * v3(fp.camera.vertical)) - origin);
+
+        out.originPix[dst] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(idx));
+        out.direction[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        out.throughput[dst] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        radiance[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    warpStatAdd(&stats[STAT_PATHS], generated);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Closest-hit traversal of queue `in` (count read from device memory).  Persistent warps pull 32
+// consecutive paths at a time from a global cursor.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_closest(
+    const SceneDevice    scene,
+    const PathQueue      in,
+    const std::uint32_t* __restrict__ inCount,
+    std::uint32_t*       fetchCursor,
+    HitRecord*           hits,
+    unsigned long long*  stats)
+{
+    const std::uint32_t n = *inCount;
+    std::uint32_t       nodes = 0, tris = 0, rays = 0;
+    while (true)
+    {
+        std::uint32_t base = 0;
+        if (laneId() == 0) base = atomicAdd(fetchCursor, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const std::uint32_t i = base + laneId();
+        if (i < n)
+        {
+            const float4 o = in.originPix[i];
+            const float4 d = in.direction[i];
+            HitRecord    hit;
+            traverseBvh<false>(scene.nodes, scene.tris, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 10000.0f /* T_MAX, wgsl:73 */, hit, nodes, tris);
+            hits[i] = hit;
+            ++rays;
+        }
+    }
+    warpStatAdd(&stats[STAT_CLOSEST_RAYS], rays);
+    warpStatAdd(&stats[STAT_CLOSEST_NODES], nodes);
+    warpStatAdd(&stats[STAT_CLOSEST_TRIS], tris);
+}
+
+// skyRadiance, wgsl:248-275 (miss path; no solar disk term).
+__device__ __forceinline__ float skyRadianceChannel(const rf_sky_state& sky, const float theta, const float gamma, const int ch)
+{
+    const float  r = sky.sky_radiances[ch];
+    const float* p = sky.params + 9 * ch;
+    const float  cosGamma = cosf(gamma);
+    const float  cosGamma2 = cosGamma * cosGamma;
+    const float  cosTheta = fabsf(cosf(theta));
+    const float  expM = expf(p[4] * gamma);
+    const float  rayM = cosGamma2;
+    const float  mieMLhs = 1.0f + cosGamma2;
+    const float  mieMRhs = powf(1.0f + p[8] * p[8] - 2.0f * p[8] * cosGamma, 1.5f);
+    const float  mieM = __fdiv_rn(mieMLhs, mieMRhs);
+    const float  zenith = __fsqrt_rn(cosTheta);
+    const float  radianceLhs = 1.0f + p[0] * expf(__fdiv_rn(p[1], cosTheta + 0.01f));
+    const float  radianceRhs = p[2] + p[3] * expM + p[5] * rayM + p[6] * mieM + p[7] * zenith;
+    return r * (radianceLhs * radianceRhs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shading of queue `in` after k_closest.  Misses add the sky and retire; hits fetch attributes and
+// albedo, compute the NEE contribution and the scattered ray, and are appended to `out`.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
+    const FrameParams    fp,
+    const SceneDevice    scene,
+    const PathQueue      in,
+    const std::uint32_t* __restrict__ inCount,
+    const HitRecord* __restrict__ hits,
+    PathQueue            out,
+    std::uint32_t*       outCount,
+    float4*              radiance)
+{
+    const std::uint32_t n = *inCount;
+    const std::uint32_t nPadded = (n + 31u) & ~31u;
+    const V3            sunDir = v3(fp.sky.sun_direction);
+    for (std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPadded; i += gridDim.x * blockDim.x)
+    {
+        const bool live = i < n;
+        bool       isHit = false;
+        HitRecord  hit{};
+        float4     oPix = make_float4(0.f, 0.f, 0.f, 0.f), thr = oPix, dir = oPix;
+        if (live)
+        {
+            hit = hits[i];
+            oPix = in.originPix[i];
+            thr = in.throughput[i];
+            isHit = hit.tri != RF_NO_HIT;
+            if (!isHit)
+            {
+                dir = in.direction[i];
+            }
+        }
+        const std::uint32_t idx = __float_as_uint(oPix.w);
+
+        if (live && !isHit)
+        {
+            // rayColor miss branch, wgsl:212-229.
+            const V3    v = v3(dir.x, dir.y, dir.z);
+            const float theta = acosf(v.y);
+            float       cosSun = dot(v, sunDir);
+            cosSun = fminf(fmaxf(cosSun, -1.0f), 1.0f);
+            const float gamma = acosf(cosSun);
+            const V3    sky = v3(
+                skyRadianceChannel(fp.sky, theta, gamma, 0),
+                skyRadianceChannel(fp.sky, theta, gamma, 1),
+                skyRadianceChannel(fp.sky, theta, gamma, 2));
+            float4 rad = radiance[idx];
+            rad.x += thr.x * sky.x, rad.y += thr.y * sky.y, rad.z += thr.z * sky.z;
+            radiance[idx] = rad;
+        }
+
+        const std::uint32_t dst = warpAppend(outCount, isHit);
+        if (!isHit) continue;
+
+        // Intersection of the final (closest) accepted triangle, wgsl:393-400.
+        const V3     p = hitPoint(scene.tris, hit);
+        const float  b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
+        const float4 a0 = ldg4(scene.vattr + 5 * hit.tri + 0);
+        const float4 a1 = ldg4(scene.vattr + 5 * hit.tri + 1);
+        const float4 a2 = ldg4(scene.vattr + 5 * hit.tri + 2);
+        const float4 a3 = ldg4(scene.vattr + 5 * hit.tri + 3);
+        const float4 a4 = ldg4(scene.vattr + 5 * hit.tri + 4);
+        const V3     nrm = (b0 * v3(a0.x, a0.y, a0.z) + b1 * v3(a1.x, a1.y, a1.z)) + b2 * v3(a2.x, a2.y, a2.z);
+        const float  tu = (b0 * a3.x + b1 * a3.z) + b2 * a4.x;
+        const float  tv = (b0 * a3.y + b1 * a3.w) + b2 * a4.y;
+        std::uint32_t texIdx = __float_as_uint(a4.z);
+        texIdx = min(texIdx, fp.numTextures - 1u); // robust buffer access
+
+        // textureLookup, wgsl:553-565.
+        const uint4         desc = scene.texDesc[texIdx];
+        const float         fu = wgslFract(tu), fv = wgslFract(tv);
+        const std::uint32_t tj = static_cast<std::uint32_t>(fu * static_cast<float>(desc.x));
+        const std::uint32_t ti = static_cast<std::uint32_t>(fv * static_cast<float>(desc.y));
+        std::uint64_t       texel = static_cast<std::uint64_t>(desc.z) + static_cast<std::uint64_t>(ti * desc.x + tj);
+        texel = texel < fp.numTexels ? texel : fp.numTexels - 1u; // robust buffer access clamps
+        const std::uint32_t bgra = __ldg(scene.texels + texel);
+        const V3            albedo = v3(scene.srgbLut[(bgra >> 16) & 0xFFu], scene.srgbLut[(bgra >> 8) & 0xFFu], scene.srgbLut[bgra & 0xFFu]);
+
+        // Per-pixel sample (the same vec2 for every decision of the path, wgsl:194,209).
+        const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
+        const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+        const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+        const float         ux = lut.ux[bn.x];
+        const float         cosPhi = lut.cosPhi[bn.y], sinPhi = lut.sinPhi[bn.y];
+
+        // sampleSolarDiskDirection -> directionInCone, wgsl:288-292,569-579.
+        const float cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
+        const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+        const V3    lightDir = onbTransform(sunDir, v3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+
+        // rayColor hit branch, wgsl:191-203.
+        const float FRAC_1_PI = 0.31830987f;
+        const V3    lightIntensity = v3(fp.sky.solar_radiances[0], fp.sky.solar_radiances[1], fp.sky.solar_radiances[2]);
+        const V3    brdf = albedo * FRAC_1_PI;
+        const V3    reflectance = brdf * dot(nrm, lightDir);
+        const V3    throughput = v3(thr.x, thr.y, thr.z);
+        const V3    contribution = (throughput * lightIntensity) * reflectance;
+
+        // evalImplicitLambertian -> directionInCosineWeightedHemisphere, wgsl:295-301,583-592.
+        const float hemiSin = __fsqrt_rn(1.0f - ux);
+        const V3    wi = onbTransform(nrm, v3(cosPhi * hemiSin, sinPhi * hemiSin, __fsqrt_rn(ux)));
+        const V3    nextThroughput = throughput * albedo;
+
+        out.originPix[dst] = make_float4(p.x, p.y, p.z, oPix.w);
+        out.direction[dst] = make_float4(wi.x, wi.y, wi.z, 0.0f);
+        out.throughput[dst] = make_float4(nextThroughput.x, nextThroughput.y, nextThroughput.z, 0.0f);
+        out.contribution[dst] = make_float4(contribution.x, contribution.y, contribution.z, 0.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shadow rays of queue `q` (every entry is a surface hit): direction = per-pixel sun sample,
+// visibility by any-hit traversal, then radiance += contribution * visibility * SOLAR_INV_PDF.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_shadow(
+    const FrameParams    fp,
+    const SceneDevice    scene,
+    const PathQueue      q,
+    const std::uint32_t* __restrict__ count,
+    std::uint32_t*       fetchCursor,
+    float4*              radiance,
+    unsigned long long*  stats)
+{
+    const std::uint32_t n = *count;
+    const V3            sunDir = v3(fp.sky.sun_direction);
+    std::uint32_t       nodes = 0, tris = 0, rays = 0;
+    while (true)
+    {
+        std::uint32_t base = 0;
+        if (laneId() == 0) base = atomicAdd(fetchCursor, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const std::uint32_t i = base + laneId();
+        if (i < n)
+        {
+            const float4        oPix = q.originPix[i];
+            const std::uint32_t idx = __float_as_uint(oPix.w);
+            const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
+            const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+            const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+            const float         ux = lut.ux[bn.x];
+            const float         cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
+            const float         sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+            const V3            lightDir = onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
+
+            HitRecord  hit;
+            const bool occluded = traverseBvh<true>(scene.nodes, scene.tris, v3(oPix.x, oPix.y, oPix.z), lightDir, 10000.0f, hit, nodes, tris);
+            const float vis = occluded ? 0.0f : 1.0f;
+            const float4 c = q.contribution[i];
+            float4       rad = radiance[idx];
+            rad.x += c.x * vis * fp.solarInvPdf;
+            rad.y += c.y * vis * fp.solarInvPdf;
+            rad.z += c.z * vis * fp.solarInvPdf;
+            radiance[idx] = rad;
+            ++rays;
+        }
+    }
+    warpStatAdd(&stats[STAT_SHADOW_RAYS], rays);
+    warpStatAdd(&stats[STAT_SHADOW_NODES], nodes);
+    warpStatAdd(&stats[STAT_SHADOW_TRIS], tris);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_THREADS) k_accumulate(
+    const FrameParams fp,
+    const std::uint32_t* __restrict__ ownedTiles,
+    const float4* __restrict__ radiance,
+    float4*           image)
+{
+    const std::uint32_t total = fp.numOwnedTiles * TILE_PIXELS;
+    for (std::uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x)
+    {
+        std::uint32_t px, py;
+        if (!slotToPixel(fp, ownedTiles, slot, px, py)) continue;
+        const std::uint32_t idx = py * fp.width + px;
+        const float4        r = radiance[idx];
+        float4              im = image[idx];
+        im.x += r.x, im.y += r.y, im.z += r.z;
+        image[idx] = im;
+    }
+}
+
+// acesFilmic, wgsl:278-285.
+__device__ __forceinline__ float acesFilmic(const float x)
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    const float y = __fdiv_rn(x * (a * x + b), x * (c * x + d) + e);
+    return fminf(fmaxf(y, 0.0f), 1.0f);
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS) k_display(
+    const std::uint32_t numPixels,
+    const float4* __restrict__ image,
+    const float       accumulated,
+    const float       exposure,
+    std::uint32_t*    outBgra)
+{
+    for (std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numPixels; i += gridDim.x * blockDim.x)
+    {
+        const float4 im = image[i];
+        const float  rgb[3] = {
+            powf(acesFilmic(exposure * __fdiv_rn(im.x, accumulated)), 1.0f / 2.2f),
+            powf(acesFilmic(exposure * __fdiv_rn(im.y, accumulated)), 1.0f / 2.2f),
+            powf(acesFilmic(exposure * __fdiv_rn(im.z, accumulated)), 1.0f / 2.2f)};
+        std::uint32_t q[3];
+        for (int c = 0; c < 3; ++c)
+        {
+            float v = rgb[c];
+            v = (v != v) ? 0.0f : fminf(fmaxf(v, 0.0f), 1.0f); // unorm conversion: NaN -> 0, clamp, round
+            q[c] = static_cast<std::uint32_t>(v * 255.0f + 0.5f);
+        }
+        outBgra[i] = q[2] | (q[1] << 8) | (q[0] << 16) | (255u << 24);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scene upload: repack the reference layouts into the traversal layouts (see traversal.cuh).
+__global__ void k_pack_nodes(const rf_bvh_node* __restrict__ src, const std::uint64_t n, float4* dst)
+{
+    for (std::uint64_t i = blockIdx.x * static_cast<std::uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<std::uint64_t>(gridDim.x) * blockDim.x)
+    {
+        const rf_bvh_node   s = src[i];
+        const bool          leaf = s.triangle_count > 0u;
+        const std::uint32_t A = leaf ? s.triangles_offset : s.second_child_offset;
+        const std::uint32_t B = leaf ? ((s.triangle_count << 2) | 3u) : s.split_axis;
+        dst[2 * i + 0] = make_float4(s.aabb_min[0], s.aabb_min[1], s.aabb_min[2], s.aabb_max[0]);
+        dst[2 * i + 1] = make_float4(s.aabb_max[1], s.aabb_max[2], __uint_as_float(A), __uint_as_float(B));
+    }
+}
+
+// `src` = triangles with `strideFloats` floats per vertex (4 for PositionAttribute, 3 for Positions).
+__global__ void k_pack_triangles(const float* __restrict__ src, const int strideFloats, const std::uint64_t n, float4* dst)
+{
+    for (std::uint64_t i = blockIdx.x * static_cast<std::uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<std::uint64_t>(gridDim.x) * blockDim.x)
+    {
+        const float* t = src + i * 3 * strideFloats;
+        const V3     v0 = v3(t), v1 = v3(t + strideFloats), v2 = v3(t + 2 * strideFloats);
+        const V3     e1 = v1 - v0, e2 = v2 - v0;
+        const V3     nrm = normalize(cross(e1, e2)); // wgsl:513 / ray_intersection.cpp:80
+        dst[3 * i + 0] = make_float4(v0.x, v0.y, v0.z, e1.x);
+        dst[3 * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+        dst[3 * i + 2] = make_float4(e2.z, nrm.x, nrm.y, nrm.z);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bvh-visualizer pixel loop (bvh-visualizer/main.cpp:60-78) and the batched rayIntersectBvh.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_visualizer(
+    const float4* __restrict__ nodes,
+    const float4* __restrict__ tris,
+    const rf_camera     camera,
+    const std::uint32_t width,
+    const std::uint32_t height,
+    const float         rayTMax,
+    std::uint32_t*      outNodes)
+{
+    // 8x4 pixel block per warp, blocks in row-major order.
+    const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
+    const std::uint32_t totalWarps = blocksX * blocksY;
+    for (std::uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < totalWarps; w += (gridDim.x * blockDim.x) >> 5)
+    {
+        const std::uint32_t j = (w % blocksX) * 8u + (laneId() & 7u);
+        const std::uint32_t i = (w / blocksX) * 4u + (laneId() >> 3);
+        if (j >= width || i >= height) continue;
+        const float u = __fdiv_rn(static_cast<float>(j), static_cast<float>(width));
+        const float v = 1.0f - __fdiv_rn(static_cast<float>(i + 1u), static_cast<float>(height));
+        // generateCameraRay, camera.cpp:44-51.
+        const V3 origin = v3(camera.origin);
+        const V3 dir = normalize(((v3(camera.lower_left_corner) + v3(camera.horizontal) * u) + v3(camera.vertical) * v) - origin);
+        HitRecord     hit;
+        std::uint32_t visited = 0, tested = 0;
+        traverseBvh<false>(nodes, tris, origin, dir, rayTMax, hit, visited, tested);
+        outNodes[i * width + j] = visited;
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS) k_intersect_batch(
+    const float4* __restrict__ nodes,
+    const float4* __restrict__ tris,
+    const float* __restrict__ rays,
+    const std::uint64_t numRays,
+    const float         rayTMax,
+    std::uint8_t*       outHit,
+    float4*             outPT,
+    std::uint32_t*      outNodes)
+{
+    for (std::uint64_t i = blockIdx.x * static_cast<std::uint64_t>(blockDim.x) + threadIdx.x; i < numRays;
+         i += static_cast<std::uint64_t>(gridDim.x) * blockDim.x)
+    {
+        const float*  r = rays + 6 * i;
+        HitRecord     hit;
+        std::uint32_t visited = 0, tested = 0;
+        const bool    didHit = traverseBvh<false>(nodes, tris, v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), rayTMax, hit, visited, tested);
+        if (outHit) outHit[i] = didHit ? 1 : 0;
+        if (outPT)
+        {
+            float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (didHit)
+            {
+                const V3 p = hitPoint(tris, hit);
+                pt = make_float4(p.x, p.y, p.z, hit.t);
+            }
+            outPT[i] = pt;
+        }
+        if (outNodes) outNodes[i] = visited;
+    }
+}
+} // namespace rfb200
