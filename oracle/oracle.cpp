@@ -579,8 +579,8 @@ void oracle_intersect_batch(
 }
 
 // bvh-visualizer pixel loop (bvh-visualizer/main.cpp:60-78); returns loop wall time in seconds.
-double oracle_bvh_visualizer(
-    const void* nodes, const float* tris, const float* cam19, int width, int height, float rayTMax,
+double oracle_bvh_visualizer_rows(
+    const void* nodes, const float* tris, const float* cam19, int width, int height, int rowBegin, int rowEnd, float rayTMax,
     std::uint32_t* outNodes, int numThreads)
 {
     SceneView scene{};
@@ -590,7 +590,7 @@ double oracle_bvh_visualizer(
     Camera camera;
     std::memcpy(&camera, cam19, sizeof(Camera));
     const auto t0 = std::chrono::steady_clock::now();
-    parallelRows(0, height, numThreads, [&](int i, int) {
+    parallelRows(rowBegin, rowEnd, numThreads, [&](int i, int) {
         for (int j = 0; j < width; ++j)
         {
             const float   u = static_cast<float>(j) / static_cast<float>(width);
@@ -602,6 +602,13 @@ double oracle_bvh_visualizer(
         }
     });
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+double oracle_bvh_visualizer(
+    const void* nodes, const float* tris, const float* cam19, int width, int height, float rayTMax,
+    std::uint32_t* outNodes, int numThreads)
+{
+    return oracle_bvh_visualizer_rows(nodes, tris, cam19, width, height, 0, height, rayTMax, outNodes, numThreads);
 }
 
 float oracle_sky_radiance(const float* skyState40, float theta, float gamma, std::uint32_t channel)

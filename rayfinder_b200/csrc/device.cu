@@ -188,7 +188,9 @@ struct rf_renderer
     // timing
     struct Timed
     {
-        cudaEvent_t begin, end;
+        cudaEvent_t              begin = nullptr, end = nullptr;
+        std::vector<cudaEvent_t> stages; // recorded between stages when stage timing is on
+        std::uint32_t            stagesUsed = 0, bounces = 0;
     };
     std::vector<Timed>  eventPool;
     std::deque<Timed>   pending;
@@ -196,31 +198,26 @@ struct rf_renderer
     double              totalMs = 0.0;
     std::uint64_t       frames = 0;
     bool                stageTiming = false;
-    std::vector<cudaEvent_t> stageEvents;
     double              msClosest = 0, msShadow = 0, msShade = 0, msOther = 0;
 
     ~rf_renderer()
     {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
-        for (auto& t : eventPool)
-        {
+        const auto destroy = [](Timed& t) {
             cudaEventDestroy(t.begin);
             cudaEventDestroy(t.end);
-        }
-        for (auto& t : pending)
-        {
-            cudaEventDestroy(t.begin);
-            cudaEventDestroy(t.end);
-        }
-        for (auto e : stageEvents) cudaEventDestroy(e);
+            for (auto e : t.stages) cudaEventDestroy(e);
+        };
+        for (auto& t : eventPool) destroy(t);
+        for (auto& t : pending) destroy(t);
     }
 
     void drainTimings(bool wait)
     {
         while (!pending.empty())
         {
-            Timed t = pending.front();
+            Timed& t = pending.front();
             if (wait)
             {
                 cudaEventSynchronize(t.end);
@@ -235,8 +232,28 @@ struct rf_renderer
             durationsMs.push_back(ms);
             if (durationsMs.size() > 30) durationsMs.pop_front(); // reference_path_tracer.cpp:689-693
             totalMs += ms;
+            if (t.stagesUsed == 3 + 3 * t.bounces)
+            {
+                // stage events: [0] before raygen, [1] after raygen, then (closest, shade, shadow) per bounce,
+                // then after accumulate.
+                const auto span = [&](std::uint32_t a, std::uint32_t b) {
+                    float x = 0.f;
+                    cudaEventElapsedTime(&x, t.stages[a], t.stages[b]);
+                    return static_cast<double>(x);
+                };
+                msOther += span(0, 1);
+                std::uint32_t e = 1;
+                for (std::uint32_t b = 0; b < t.bounces; ++b, e += 3)
+                {
+                    msClosest += span(e, e + 1);
+                    msShade += span(e + 1, e + 2);
+                    msShadow += span(e + 2, e + 3);
+                }
+                msOther += span(e, e + 1);
+            }
+            t.stagesUsed = 0;
             pending.pop_front();
-            eventPool.push_back(t);
+            eventPool.push_back(std::move(t));
         }
     }
 
@@ -442,7 +459,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     rf_renderer::Timed t{};
     if (!r->eventPool.empty())
     {
-        t = r->eventPool.back();
+        t = std::move(r->eventPool.back());
         r->eventPool.pop_back();
     }
     else
@@ -450,17 +467,18 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         RF_CUDA(cudaEventCreate(&t.begin));
         RF_CUDA(cudaEventCreate(&t.end));
     }
-    std::size_t stageIdx = 0;
-    const auto  stageMark = [&]() -> cudaError_t {
+    t.stagesUsed = 0;
+    t.bounces = fp.numBounces;
+    const auto stageMark = [&]() -> cudaError_t {
         if (!r->stageTiming) return cudaSuccess;
-        if (stageIdx >= r->stageEvents.size())
+        if (t.stagesUsed >= t.stages.size())
         {
             cudaEvent_t e;
             const cudaError_t err = cudaEventCreate(&e);
             if (err != cudaSuccess) return err;
-            r->stageEvents.push_back(e);
+            t.stages.push_back(e);
         }
-        return cudaEventRecord(r->stageEvents[stageIdx++], s);
+        return cudaEventRecord(t.stages[t.stagesUsed++], s);
     };
 
     RF_CUDA(cudaEventRecord(t.begin, s));
@@ -499,35 +517,10 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     RF_CUDA(stageMark());
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventRecord(t.end, s));
-    r->pending.push_back(t);
+    r->pending.push_back(std::move(t));
     r->frames++;
     r->accumulated = std::min(r->accumulated + 1, spp); // reference_path_tracer.cpp:590-591
 
-    if (r->stageTiming)
-    {
-        RF_CUDA(cudaStreamSynchronize(s));
-        // events: [0]=before raygen, [1]=after raygen, then per bounce 3, then final
-        float ms = 0.f;
-        std::size_t e = 0;
-        if (fp.numOwnedTiles > 0)
-        {
-            cudaEventElapsedTime(&ms, r->stageEvents[0], r->stageEvents[1]);
-            r->msOther += ms;
-            e = 1;
-            for (std::uint32_t b = 0; b < fp.numBounces; ++b)
-            {
-                cudaEventElapsedTime(&ms, r->stageEvents[e], r->stageEvents[e + 1]);
-                r->msClosest += ms;
-                cudaEventElapsedTime(&ms, r->stageEvents[e + 1], r->stageEvents[e + 2]);
-                r->msShade += ms;
-                cudaEventElapsedTime(&ms, r->stageEvents[e + 2], r->stageEvents[e + 3]);
-                r->msShadow += ms;
-                e += 3;
-            }
-            cudaEventElapsedTime(&ms, r->stageEvents[e], r->stageEvents[e + 1]);
-            r->msOther += ms;
-        }
-    }
     return RF_OK;
 }
 

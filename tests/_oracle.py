@@ -1,0 +1,217 @@
+"""ctypes access to the parity oracle (oracle/liboracle.so) and to the compiled reference CPU path
+(oracle/_ref/libref_oracle.so).  TEST INFRASTRUCTURE: imported only by tests/, smoke() and bench.py's
+cpu_baseline / --impl reference legs — never by rayfinder_b200/."""
+from __future__ import annotations
+
+import ctypes as C
+import lzma
+import os
+import subprocess
+from functools import lru_cache
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+ORACLE_LIB = ORACLE_DIR / "liboracle.so"
+REF_LIB = ORACLE_DIR / "_ref" / "libref_oracle.so"
+GOLDEN = ROOT / "tests" / "golden"
+ASSETS = ROOT / "assets"
+DATA = ROOT / "rayfinder_b200" / "data"
+
+_P = C.c_void_p
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def build_oracle() -> None:
+    if not ORACLE_LIB.exists() or ORACLE_LIB.stat().st_mtime < (ORACLE_DIR / "oracle.cpp").stat().st_mtime:
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "oracle"], check=True, capture_output=True)
+
+
+class OracleScene(C.Structure):
+    _fields_ = [("nodes", _P), ("positionAttributes", _P), ("vertexAttributes", _P), ("texDesc", _P),
+                ("numTextures", C.c_uint32), ("texels", _P), ("numTexels", C.c_uint64), ("blueNoiseRg8", _P)]
+
+
+class OracleFrame(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("frameCount", C.c_uint32),
+                ("numSamplesPerPixel", C.c_uint32), ("numBounces", C.c_uint32),
+                ("accumulatedSampleCount", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
+                ("camera", C.c_float * 19), ("skyState", C.c_float * 40)]
+
+
+@lru_cache(maxsize=None)
+def oracle() -> C.CDLL:
+    build_oracle()
+    lib = C.CDLL(str(ORACLE_LIB))
+    lib.oracle_bvh_visualizer.restype = C.c_double
+    lib.oracle_bvh_visualizer.argtypes = [_P, _P, _P, C.c_int, C.c_int, C.c_float, _P, C.c_int]
+    lib.oracle_bvh_visualizer_rows.restype = C.c_double
+    lib.oracle_bvh_visualizer_rows.argtypes = [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, C.c_int]
+    lib.oracle_intersect_batch.argtypes = [_P, _P, _P, C.c_uint64, C.c_float, _P, _P, _P, C.c_int]
+    lib.oracle_create_camera.argtypes = [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P]
+    lib.oracle_ray_intersect_aabb.argtypes = [_P, _P, C.c_float]
+    lib.oracle_ray_intersect_triangle.argtypes = [_P, _P, C.c_float, _P]
+    lib.oracle_sky_radiance.restype = C.c_float
+    lib.oracle_sky_radiance.argtypes = [_P, C.c_float, C.c_float, C.c_uint32]
+    lib.oracle_solar_constants.argtypes = [_P]
+    lib.oracle_render_frame.restype = C.c_double
+    lib.oracle_render_frame.argtypes = [C.POINTER(OracleScene), C.POINTER(OracleFrame), _P, _P, _P, C.c_int]
+    lib.oracle_display.argtypes = [_P, C.c_uint64, C.c_float, C.c_float, _P]
+    return lib
+
+
+def have_ref() -> bool:
+    return REF_LIB.exists()
+
+
+@lru_cache(maxsize=None)
+def ref() -> C.CDLL:
+    lib = C.CDLL(str(REF_LIB))
+    lib.ref_bvh_build.restype = _P
+    lib.ref_bvh_build.argtypes = [_P, C.c_uint64]
+    lib.ref_bvh_num_nodes.restype = C.c_uint64
+    lib.ref_bvh_num_nodes.argtypes = [_P]
+    lib.ref_bvh_copy.argtypes = [_P, _P, _P]
+    lib.ref_bvh_free.argtypes = [_P]
+    lib.ref_create_camera.argtypes = [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P]
+    lib.ref_generate_camera_ray.argtypes = [_P, C.c_float, C.c_float, _P]
+    lib.ref_ray_intersect_aabb.argtypes = [_P, _P, C.c_float]
+    lib.ref_ray_intersect_triangle.argtypes = [_P, _P, C.c_float, _P]
+    lib.ref_intersect_batch.argtypes = [_P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint64, C.c_float, _P, _P, _P, C.c_int]
+    lib.ref_bvh_visualizer.restype = C.c_double
+    lib.ref_bvh_visualizer.argtypes = [_P, C.c_uint64, _P, C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, C.c_int]
+    lib.ref_sky_state_new.argtypes = [C.c_float, C.c_float, _P, _P]
+    lib.ref_sky_state_radiance.restype = C.c_float
+    lib.ref_sky_state_radiance.argtypes = [_P, C.c_float, C.c_float, C.c_int]
+    lib.ref_blue_noise.restype = C.POINTER(C.c_uint8)
+    lib.ref_blue_noise.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    return lib
+
+
+def num_threads() -> int:
+    return max(1, len(os.sched_getaffinity(0)))
+
+
+def blue_noise_rg8() -> np.ndarray:
+    return np.fromfile(DATA / "blue_noise_128x128_rg8.bin", dtype=np.uint8)
+
+
+# ---- scenes ------------------------------------------------------------------------------------------
+def duck_pt_bytes() -> bytes:
+    """Duck.pt baked from the reference's assets/Duck.glb by rayfinder_b200.baker (committed as a fixture,
+    see tests/golden/make_golden.py)."""
+    return lzma.decompress((GOLDEN / "Duck.pt.xz").read_bytes())
+
+
+def triangles9(pt) -> np.ndarray:
+    """nlrs::Positions view (n, 9) of PtFormat.bvh_position_attributes."""
+    return np.ascontiguousarray(pt.bvh_position_attributes).view("<f4").reshape(-1, 9)
+
+
+def tex_desc(textures) -> tuple[np.ndarray, np.ndarray]:
+    """(descriptors (n,3) u32, concatenated texels) as packed by reference_path_tracer.cpp:209-270."""
+    desc, off = [], 0
+    for t in textures:
+        desc.append((t.shape[1], t.shape[0], off))
+        off += t.size
+    return np.array(desc, dtype=np.uint32), np.concatenate([np.ascontiguousarray(t).reshape(-1) for t in textures]).astype("<u4")
+
+
+# ---- oracle wrappers ---------------------------------------------------------------------------------
+def oracle_node_counts(nodes, tris9, cam19, width, height, t_max, threads=None, rows=None):
+    out = np.zeros((height, width), dtype=np.uint32)
+    cam19 = np.ascontiguousarray(cam19, dtype=np.float32)
+    r0, r1 = rows if rows else (0, height)
+    secs = oracle().oracle_bvh_visualizer_rows(_ptr(nodes), _ptr(tris9), _ptr(cam19), width, height, r0, r1, t_max, _ptr(out),
+                                               threads or num_threads())
+    return out, secs
+
+
+def ref_node_counts(nodes, tris9, cam19, width, height, t_max, threads=None, rows=None):
+    out = np.zeros((height, width), dtype=np.uint32)
+    cam19 = np.ascontiguousarray(cam19, dtype=np.float32)
+    r0, r1 = rows if rows else (0, height)
+    secs = ref().ref_bvh_visualizer(_ptr(nodes), nodes.size, _ptr(tris9), tris9.shape[0], _ptr(cam19), width, height,
+                                    r0, r1, t_max, _ptr(out), threads or num_threads())
+    return out, secs
+
+
+def _batch(fn_call, n):
+    hit = np.zeros(n, dtype=np.uint8)
+    p_t = np.zeros((n, 4), dtype=np.float32)
+    visited = np.zeros(n, dtype=np.uint32)
+    fn_call(hit, p_t, visited)
+    return hit.astype(bool), p_t, visited
+
+
+def oracle_intersect(nodes, tris9, rays, t_max, threads=None):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+    return _batch(lambda h, p, v: oracle().oracle_intersect_batch(
+        _ptr(nodes), _ptr(tris9), _ptr(rays), rays.shape[0], t_max, _ptr(h), _ptr(p), _ptr(v), threads or num_threads()), rays.shape[0])
+
+
+def ref_intersect(nodes, tris9, rays, t_max, threads=None):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+    return _batch(lambda h, p, v: ref().ref_intersect_batch(
+        _ptr(nodes), nodes.size, _ptr(tris9), tris9.shape[0], _ptr(rays), rays.shape[0], t_max, _ptr(h), _ptr(p), _ptr(v),
+        threads or num_threads()), rays.shape[0])
+
+
+COUNTER_NAMES = ("paths", "closest_rays", "shadow_rays", "closest_nodes_visited", "closest_triangles_tested",
+                 "shadow_nodes_visited", "shadow_triangles_tested")
+
+
+class OracleRenderer:
+    """Oracle B driver with the accumulation bookkeeping of reference_path_tracer.cpp:556-591."""
+
+    def __init__(self, pt, width, height, cam19, sky40, spp, bounces, rank=0, world=1, threads=None):
+        self.nodes = np.ascontiguousarray(pt.bvh_nodes)
+        self.pos = np.ascontiguousarray(pt.triangle_position_attributes)
+        self.vat = np.ascontiguousarray(pt.triangle_vertex_attributes)
+        self.desc, self.texels = tex_desc(pt.base_color_textures)
+        self.bn = blue_noise_rg8()
+        self.scene = OracleScene(_ptr(self.nodes), _ptr(self.pos), _ptr(self.vat), _ptr(self.desc), len(self.desc),
+                                 _ptr(self.texels), self.texels.size, _ptr(self.bn))
+        self.width, self.height, self.spp, self.bounces = width, height, spp, bounces
+        self.cam19 = np.ascontiguousarray(cam19, dtype=np.float32)
+        self.sky40 = np.ascontiguousarray(sky40, dtype=np.float32)
+        self.rank, self.world = rank, world
+        self.threads = threads or num_threads()
+        self.frame_count = 0
+        self.accumulated = 0
+        self.image = np.zeros((height, width, 4), dtype=np.float32)
+        self.counters = np.zeros(9, dtype=np.uint64)
+        self.path_lengths = np.zeros((height, width), dtype=np.uint8)
+        self.seconds = 0.0
+
+    def render(self):
+        fr = OracleFrame(self.width, self.height, self.frame_count, self.spp, self.bounces, self.accumulated,
+                         self.rank, self.world, (C.c_float * 19)(*self.cam19), (C.c_float * 40)(*self.sky40))
+        self.frame_count += 1
+        self.seconds += oracle().oracle_render_frame(C.byref(self.scene), C.byref(fr), _ptr(self.image), _ptr(self.counters),
+                                                     _ptr(self.path_lengths), self.threads)
+        self.accumulated = min(self.accumulated + 1, self.spp)
+
+    def stats(self) -> dict:
+        return {k: int(v) for k, v in zip(COUNTER_NAMES, self.counters)}
+
+    def display(self, exposure: float) -> np.ndarray:
+        out = np.zeros((self.height, self.width), dtype=np.uint32)
+        oracle().oracle_display(_ptr(self.image), self.width * self.height, float(max(self.accumulated, 1)), exposure, _ptr(out))
+        return out
+
+
+def rmse(a: np.ndarray, b: np.ndarray) -> float:
+    """sqrt(mean over pixels x 3 channels of (delta)^2) on linear HDR; NaN == NaN counts as equal."""
+    a3, b3 = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    d = a3 - b3
+    both_nan = np.isnan(a3) & np.isnan(b3)
+    d[both_nan] = 0.0
+    same_inf = np.isinf(a3) & (a3 == b3)
+    d[same_inf] = 0.0
+    return float(np.sqrt(np.mean(d * d)))

@@ -1,0 +1,39 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def duck_pt():
+    import _oracle as O
+    import rayfinder_b200 as rf
+
+    return rf.PtFormat.loads(O.duck_pt_bytes())
+
+
+@pytest.fixture(scope="session")
+def sponza_pt():
+    import _oracle as O
+    import rayfinder_b200 as rf
+
+    path = O.ASSETS / "Sponza.pt"
+    if not path.exists():
+        pytest.skip("assets/Sponza.pt not baked (run __graft_entry__.build() where /root/reference is mounted)")
+    return rf.PtFormat.load(path)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import _oracle as O
+
+    return {p.stem: np.load(p) for p in O.GOLDEN.glob("*.npz")}
