@@ -50,9 +50,10 @@ def parse_args():
 def load_scene():
     import rayfinder_b200 as rf
 
-    path = ROOT / "assets" / "Sponza.pt"
-    if path.exists():
-        return rf.PtFormat.load(path), "Sponza.pt"
+    from rayfinder_b200 import assets as rfa
+
+    if rfa.scene_path("Sponza") is not None:
+        return rfa.load_scene("Sponza"), "Sponza.pt"
     import _oracle as O  # fixture loader only (no oracle code runs)
 
     return rf.PtFormat.loads(O.duck_pt_bytes()), "Duck.pt (Sponza.pt not baked on this box)"

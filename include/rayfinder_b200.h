@@ -246,6 +246,10 @@ rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out);
 rf_status rf_renderer_reset_stats(rf_renderer* r);
 /* Per-stage CUDA-event timing (adds event records between stages; off by default). */
 rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled);
+/* Scheduling knobs of the persistent traversal kernels (results never depend on them): a triangle round
+ * runs once `tri_min` lanes of a warp have a triangle pending, idle lanes are refilled once `refill_min`
+ * are idle, `blocks_per_sm` persistent 256-thread blocks are launched per SM.  0 keeps a value. */
+rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refill_min, uint32_t blocks_per_sm);
 
 /* ---- the CPU traversal twin: nlrs::rayIntersectBvh (common/ray_intersection.hpp:43-49) --------- */
 

@@ -358,6 +358,9 @@ class ReferencePathTracer:
     def set_stage_timing(self, enabled: bool) -> None:
         check(lib().rf_renderer_set_stage_timing(self._handle, int(enabled)))
 
+    def set_tuning(self, tri_min: int = 0, refill_min: int = 0, blocks_per_sm: int = 0) -> None:
+        check(lib().rf_renderer_set_tuning(self._handle, tri_min, refill_min, blocks_per_sm))
+
 
 class TraversalScene:
     """Device-resident (bvhNodes, triangles) for the GPU twin of ``rayIntersectBvh``."""

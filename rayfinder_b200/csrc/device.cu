@@ -7,6 +7,8 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -78,13 +80,19 @@ rf_status selectDevice(int32_t device, int& outDevice, int& numSms)
 // increase along any descent (=> termination), leaf ranges lie inside the triangle array, interior
 // split axes are 0..2, and the deepest leaf fits the reference's 32-entry stack
 // (ray_intersection.cpp:148,194; wgsl:327,375).
-rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uint64_t numTriangles)
+rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uint64_t numTriangles, bool& ordered)
 {
+    ordered = true;
     if (numNodes == 0 || numNodes >= 0x7FFFFFFFull) return setError(RF_ERROR_INVALID_ARGUMENT, "BVH must have between 1 and 2^31-1 nodes.");
     if (numTriangles >= (1ull << 30)) return setError(RF_ERROR_INVALID_ARGUMENT, "Too many triangles.");
     for (std::uint64_t i = 0; i < numNodes; ++i)
     {
         const rf_bvh_node& n = nodes[i];
+        for (int a = 0; a < 3; ++a)
+        {
+            // finite and min <= max on every axis: the precondition of the NaN-free slab test (traversal.cuh)
+            if (!(std::isfinite(n.aabb_min[a]) && std::isfinite(n.aabb_max[a]) && n.aabb_min[a] <= n.aabb_max[a])) ordered = false;
+        }
         if (n.triangle_count > 0)
         {
             if (static_cast<std::uint64_t>(n.triangles_offset) + n.triangle_count > numTriangles)
@@ -121,6 +129,15 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
     return RF_OK;
 }
 
+// Scheduling knobs of the persistent traversal loop; RF_TRI_MIN / RF_REFILL_MIN override for sweeps.
+TraceTuning defaultTuning()
+{
+    TraceTuning t{8u, 4u};
+    if (const char* e = std::getenv("RF_TRI_MIN")) t.triMin = static_cast<std::uint32_t>(std::max(1, std::atoi(e)));
+    if (const char* e = std::getenv("RF_REFILL_MIN")) t.refillMin = static_cast<std::uint32_t>(std::max(1, std::atoi(e)));
+    return t;
+}
+
 bool sameParams(const rf_render_parameters& a, const rf_render_parameters& b)
 {
     // RenderParameters::operator== (reference_path_tracer.hpp:42): member-wise, floats by value.
@@ -155,7 +172,10 @@ struct rf_renderer
     cudaStream_t stream = nullptr; // default stream unless rf_renderer_set_stream is called
 
     // scene
-    DeviceBuffer<float4>        nodes, tris, vattr;
+    DeviceBuffer<PackedNode>    nodes;
+    DeviceBuffer<float4>        tris, vattr;
+    bool                        ordered = true;
+    TraceTuning                 tuning = defaultTuning();
     DeviceBuffer<uint4>         texDesc;
     DeviceBuffer<std::uint32_t> texels;
     DeviceBuffer<uchar2>        blueNoise;
@@ -252,8 +272,8 @@ struct rf_renderer
                 msOther += span(e, e + 1);
             }
             t.stagesUsed = 0;
-            pending.pop_front();
             eventPool.push_back(std::move(t));
+            pending.pop_front();
         }
     }
 
@@ -295,6 +315,7 @@ struct rf_renderer
         return RF_OK;
     }
 
+    int traceBlocksPerSm = 4; // 256 threads x <=64 registers, 32 KB of shared stack per block
     int gridFor(int blocksPerSm) const { return numSms * blocksPerSm; }
 };
 
@@ -312,7 +333,8 @@ extern "C" rf_status rf_renderer_create(
         return setError(RF_ERROR_INVALID_ARGUMENT, "Scene spans must be non-empty.");
     if (scene->num_position_attributes != scene->num_vertex_attributes)
         return setError(RF_ERROR_INVALID_ARGUMENT, "positionAttributes and vertexAttributes must have the same length.");
-    rf_status st = validateBvh(scene->bvh_nodes, scene->num_bvh_nodes, scene->num_position_attributes);
+    bool      ordered = true;
+    rf_status st = validateBvh(scene->bvh_nodes, scene->num_bvh_nodes, scene->num_position_attributes, ordered);
     if (st != RF_OK) return st;
     st = validateParams(desc->render_params, desc->max_framebuffer_width, desc->max_framebuffer_height);
     if (st != RF_OK) return st;
@@ -320,6 +342,7 @@ extern "C" rf_status rf_renderer_create(
     auto r = std::make_unique<rf_renderer>();
     st = selectDevice(device, r->device, r->numSms);
     if (st != RF_OK) return st;
+    r->ordered = ordered;
 
     // Texture descriptors + concatenated texels (reference_path_tracer.cpp:209-270).
     std::vector<uint4> descs;
@@ -349,7 +372,7 @@ extern "C" rf_status rf_renderer_create(
         RF_CUDA(rawTris.allocate(numTris * 12));
         RF_CUDA(cudaMemcpy(rawNodes.ptr, scene->bvh_nodes, numNodes * sizeof(rf_bvh_node), cudaMemcpyHostToDevice));
         RF_CUDA(cudaMemcpy(rawTris.ptr, scene->position_attributes, numTris * sizeof(rf_position_attribute), cudaMemcpyHostToDevice));
-        RF_CUDA(r->nodes.allocate(2 * numNodes));
+        RF_CUDA(r->nodes.allocate(numNodes));
         RF_CUDA(r->tris.allocate(3 * numTris));
         k_pack_nodes<<<r->numSms * 4, 256>>>(rawNodes.ptr, numNodes, r->nodes.ptr);
         k_pack_triangles<<<r->numSms * 4, 256>>>(rawTris.ptr, 4, numTris, r->tris.ptr);
@@ -454,7 +477,8 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     fp.solarCosThetaMax = sc.cosThetaMax;
     fp.solarInvPdf = sc.invPdf;
 
-    SceneDevice scene{r->nodes.ptr, r->tris.ptr, r->vattr.ptr, r->texDesc.ptr, r->texels.ptr, r->blueNoise.ptr, r->lut.ptr, r->srgbLut.ptr};
+    SceneDevice scene{r->nodes.ptr, r->tris.ptr, r->vattr.ptr, r->texDesc.ptr, r->texels.ptr, r->blueNoise.ptr, r->lut.ptr, r->srgbLut.ptr,
+                      r->ordered, r->tuning};
 
     rf_renderer::Timed t{};
     if (!r->eventPool.empty())
@@ -492,7 +516,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     RF_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
 
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->gridFor(6);
+    const int gridTrace = r->gridFor(r->traceBlocksPerSm);
     RF_CUDA(stageMark());
     if (fp.numOwnedTiles > 0)
     {
@@ -505,11 +529,11 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             std::uint32_t* outCount = &ctr->queueCount[outQ];
             RF_CUDA(cudaMemsetAsync(outCount, 0, sizeof(std::uint32_t) + 0, s));
             RF_CUDA(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(ctr->fetch), s));
-            k_closest<<<gridTrace, BLOCK_THREADS, 0, s>>>(scene, r->queues[in], inCount, &ctr->fetch[0], r->hits.ptr, r->stats.ptr);
+            k_closest<<<gridTrace, TRACE_BLOCK_THREADS, 0, s>>>(scene, r->queues[in], inCount, &ctr->fetch[0], r->hits.ptr, r->stats.ptr);
             RF_CUDA(stageMark());
             k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], inCount, r->hits.ptr, r->queues[outQ], outCount, r->radiance.ptr);
             RF_CUDA(stageMark());
-            k_shadow<<<gridTrace, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[outQ], outCount, &ctr->fetch[2], r->radiance.ptr, r->stats.ptr);
+            k_shadow<<<gridTrace, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[outQ], outCount, &ctr->fetch[2], r->radiance.ptr, r->stats.ptr);
             RF_CUDA(stageMark());
         }
         k_accumulate<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, r->ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
@@ -640,13 +664,27 @@ extern "C" rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enable
     return RF_OK;
 }
 
+extern "C" rf_status rf_renderer_set_tuning(rf_renderer* r, std::uint32_t triMin, std::uint32_t refillMin, std::uint32_t blocksPerSm)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: null renderer");
+    if (triMin > 32u || refillMin > 32u || blocksPerSm > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
+    if (triMin) r->tuning.triMin = triMin;
+    if (refillMin) r->tuning.refillMin = refillMin;
+    if (blocksPerSm) r->traceBlocksPerSm = static_cast<int>(blocksPerSm);
+    return RF_OK;
+}
+
 // =================================================================================================
 struct rf_traversal_scene
 {
     int                  device = 0;
     int                  numSms = 0;
-    DeviceBuffer<float4> nodes, tris;
-    std::uint64_t        numNodes = 0, numTris = 0;
+    DeviceBuffer<PackedNode>    nodes;
+    DeviceBuffer<float4>        tris;
+    DeviceBuffer<std::uint32_t> cursor;
+    bool                        ordered = true;
+    TraceTuning                 tuning = defaultTuning();
+    std::uint64_t               numNodes = 0, numTris = 0;
 };
 
 extern "C" rf_status rf_traversal_scene_create(
@@ -658,9 +696,11 @@ extern "C" rf_status rf_traversal_scene_create(
     rf_traversal_scene** out)
 {
     if (!nodes || !triangles || !out || numTriangles == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_traversal_scene_create: null or empty argument");
-    rf_status st = validateBvh(nodes, numNodes, numTriangles);
+    bool      ordered = true;
+    rf_status st = validateBvh(nodes, numNodes, numTriangles, ordered);
     if (st != RF_OK) return st;
     auto s = std::make_unique<rf_traversal_scene>();
+    s->ordered = ordered;
     st = selectDevice(device, s->device, s->numSms);
     if (st != RF_OK) return st;
     DeviceBuffer<rf_bvh_node> rawNodes;
@@ -669,7 +709,8 @@ extern "C" rf_status rf_traversal_scene_create(
     RF_CUDA(rawTris.allocate(numTriangles * 9));
     RF_CUDA(cudaMemcpy(rawNodes.ptr, nodes, numNodes * sizeof(rf_bvh_node), cudaMemcpyHostToDevice));
     RF_CUDA(cudaMemcpy(rawTris.ptr, triangles, numTriangles * sizeof(rf_positions), cudaMemcpyHostToDevice));
-    RF_CUDA(s->nodes.allocate(2 * numNodes));
+    RF_CUDA(s->nodes.allocate(numNodes));
+    RF_CUDA(s->cursor.allocate(1));
     RF_CUDA(s->tris.allocate(3 * numTriangles));
     k_pack_nodes<<<s->numSms * 4, 256>>>(rawNodes.ptr, numNodes, s->nodes.ptr);
     k_pack_triangles<<<s->numSms * 4, 256>>>(rawTris.ptr, 3, numTriangles, s->tris.ptr);
@@ -707,9 +748,13 @@ extern "C" rf_status rf_ray_intersect_bvh(
     if (outHit) RF_CUDA(dHit.allocate(numRays));
     if (outPT) RF_CUDA(dPT.allocate(numRays));
     if (outNodes) RF_CUDA(dNodes.allocate(numRays));
-    const std::uint64_t blocksNeeded = (numRays + BLOCK_THREADS - 1) / BLOCK_THREADS;
-    const int           grid = static_cast<int>(std::min<std::uint64_t>(blocksNeeded, static_cast<std::uint64_t>(s->numSms) * 8));
-    k_intersect_batch<<<grid, BLOCK_THREADS>>>(s->nodes.ptr, s->tris.ptr, dRays.ptr, numRays, rayTMax, dHit.ptr, dPT.ptr, dNodes.ptr);
+    if (numRays >= 0xFFFFFFF0ull) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_ray_intersect_bvh: at most 2^32-16 rays per call");
+    const std::uint64_t blocksNeeded = (numRays + TRACE_BLOCK_THREADS - 1) / TRACE_BLOCK_THREADS;
+    const int           grid = static_cast<int>(std::min<std::uint64_t>(blocksNeeded, static_cast<std::uint64_t>(s->numSms) * 4));
+    RF_CUDA(cudaMemset(s->cursor.ptr, 0, sizeof(std::uint32_t)));
+    k_intersect_batch<<<grid, TRACE_BLOCK_THREADS>>>(
+        s->nodes.ptr, s->tris.ptr, s->ordered, s->tuning, dRays.ptr, static_cast<std::uint32_t>(numRays), rayTMax, s->cursor.ptr,
+        dHit.ptr, dPT.ptr, dNodes.ptr);
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaDeviceSynchronize());
     if (outHit) RF_CUDA(cudaMemcpy(outHit, dHit.ptr, numRays, cudaMemcpyDeviceToHost));
@@ -735,8 +780,10 @@ extern "C" rf_status rf_bvh_visualizer_node_counts(
     cudaEvent_t e0, e1;
     RF_CUDA(cudaEventCreate(&e0));
     RF_CUDA(cudaEventCreate(&e1));
+    RF_CUDA(cudaMemset(s->cursor.ptr, 0, sizeof(std::uint32_t)));
     RF_CUDA(cudaEventRecord(e0));
-    k_visualizer<<<s->numSms * 8, BLOCK_THREADS>>>(s->nodes.ptr, s->tris.ptr, *camera, width, height, rayTMax, dNodes.ptr);
+    k_visualizer<<<s->numSms * 4, TRACE_BLOCK_THREADS>>>(
+        s->nodes.ptr, s->tris.ptr, s->ordered, s->tuning, *camera, width, height, rayTMax, s->cursor.ptr, dNodes.ptr);
     RF_CUDA(cudaEventRecord(e1));
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaDeviceSynchronize());

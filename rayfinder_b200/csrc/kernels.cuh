@@ -48,7 +48,7 @@ struct FrameParams
 
 struct SceneDevice
 {
-    const float4*        nodes;      // 2 x float4 per node
+    const PackedNode*    nodes;      // 32 B per node
     const float4*        tris;       // 3 x float4 per triangle
     const float4*        vattr;      // 5 x float4 per triangle (VertexAttributes as-is)
     const uint4*         texDesc;    // (width, height, offset, 0)
@@ -56,6 +56,8 @@ struct SceneDevice
     const uchar2*        blueNoise;  // 128 x 128
     const SampleLutRow*  lut;        // one row per sample index
     const float*         srgbLut;    // 256
+    bool                 ordered;    // every node box finite with min <= max (enables the NaN-free slab test)
+    TraceTuning          tuning;
 };
 
 // Device counters, zeroed at the start of every frame.
@@ -76,8 +78,6 @@ enum StatSlot
     STAT_SHADOW_TRIS,
     STAT_COUNT
 };
-
-__device__ __forceinline__ std::uint32_t laneId() { return threadIdx.x & 31u; }
 
 // Warp-aggregated append: returns the slot for this lane if `pred`, using one atomic per warp.
 __device__ __forceinline__ std::uint32_t warpAppend(std::uint32_t* counter, const bool pred)
@@ -183,9 +183,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Closest-hit traversal of queue `in` (count read from device memory).  Persistent warps pull 32
-// consecutive paths at a time from a global cursor.
-__global__ void __launch_bounds__(BLOCK_THREADS) k_closest(
+// Closest-hit traversal of queue `in` (count read from device memory): rayIntersectBvh(ray, T_MAX, &hit).
+struct ClosestIO
+{
+    const PathQueue in;
+    HitRecord*      hits;
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
+    {
+        const float4 oo = in.originPix[i];
+        const float4 dd = in.direction[i];
+        o = v3(oo.x, oo.y, oo.z), d = v3(dd.x, dd.y, dd.z);
+        tmax = 10000.0f; // T_MAX, wgsl:73
+        return true;
+    }
+    __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord& hit, std::uint32_t) const { hits[i] = hit; }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_closest(
     const SceneDevice    scene,
     const PathQueue      in,
     const std::uint32_t* __restrict__ inCount,
@@ -193,25 +207,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_closest(
     HitRecord*           hits,
     unsigned long long*  stats)
 {
-    const std::uint32_t n = *inCount;
-    std::uint32_t       nodes = 0, tris = 0, rays = 0;
-    while (true)
-    {
-        std::uint32_t base = 0;
-        if (laneId() == 0) base = atomicAdd(fetchCursor, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const std::uint32_t i = base + laneId();
-        if (i < n)
-        {
-            const float4 o = in.originPix[i];
-            const float4 d = in.direction[i];
-            HitRecord    hit;
-            traverseBvh<false>(scene.nodes, scene.tris, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 10000.0f /* T_MAX, wgsl:73 */, hit, nodes, tris);
-            hits[i] = hit;
-            ++rays;
-        }
-    }
+    std::uint32_t nodes = 0, tris = 0, rays = 0;
+    ClosestIO     io{in, hits};
+    traceRays<false>(scene.nodes, scene.tris, scene.ordered, *inCount, fetchCursor, scene.tuning, io, nodes, tris, rays);
     warpStatAdd(&stats[STAT_CLOSEST_RAYS], rays);
     warpStatAdd(&stats[STAT_CLOSEST_NODES], nodes);
     warpStatAdd(&stats[STAT_CLOSEST_TRIS], tris);
@@ -350,7 +348,43 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
 // ---------------------------------------------------------------------------------------------
 // Shadow rays of queue `q` (every entry is a surface hit): direction = per-pixel sun sample,
 // visibility by any-hit traversal, then radiance += contribution * visibility * SOLAR_INV_PDF.
-__global__ void __launch_bounds__(BLOCK_THREADS) k_shadow(
+struct ShadowIO
+{
+    const FrameParams& fp;
+    const SceneDevice& scene;
+    const PathQueue    q;
+    float4*            radiance;
+    const V3           sunDir;
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
+    {
+        const float4        oPix = q.originPix[i];
+        const std::uint32_t idx = __float_as_uint(oPix.w);
+        const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
+        const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+        const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+        const float         ux = lut.ux[bn.x];
+        // sampleSolarDiskDirection -> directionInCone, wgsl:288-292,569-579
+        const float cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
+        const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+        o = v3(oPix.x, oPix.y, oPix.z);
+        d = onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
+        tmax = 10000.0f;
+        return true;
+    }
+    __device__ __forceinline__ void finish(const std::uint32_t i, const bool occluded, const HitRecord&, std::uint32_t) const
+    {
+        const std::uint32_t idx = __float_as_uint(q.originPix[i].w);
+        const float         vis = occluded ? 0.0f : 1.0f;
+        const float4        c = q.contribution[i];
+        float4              rad = radiance[idx];
+        rad.x += c.x * vis * fp.solarInvPdf;
+        rad.y += c.y * vis * fp.solarInvPdf;
+        rad.z += c.z * vis * fp.solarInvPdf;
+        radiance[idx] = rad;
+    }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_shadow(
     const FrameParams    fp,
     const SceneDevice    scene,
     const PathQueue      q,
@@ -359,40 +393,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shadow(
     float4*              radiance,
     unsigned long long*  stats)
 {
-    const std::uint32_t n = *count;
-    const V3            sunDir = v3(fp.sky.sun_direction);
-    std::uint32_t       nodes = 0, tris = 0, rays = 0;
-    while (true)
-    {
-        std::uint32_t base = 0;
-        if (laneId() == 0) base = atomicAdd(fetchCursor, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const std::uint32_t i = base + laneId();
-        if (i < n)
-        {
-            const float4        oPix = q.originPix[i];
-            const std::uint32_t idx = __float_as_uint(oPix.w);
-            const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
-            const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
-            const SampleLutRow& lut = scene.lut[fp.sampleIndex];
-            const float         ux = lut.ux[bn.x];
-            const float         cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
-            const float         sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
-            const V3            lightDir = onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
-
-            HitRecord  hit;
-            const bool occluded = traverseBvh<true>(scene.nodes, scene.tris, v3(oPix.x, oPix.y, oPix.z), lightDir, 10000.0f, hit, nodes, tris);
-            const float vis = occluded ? 0.0f : 1.0f;
-            const float4 c = q.contribution[i];
-            float4       rad = radiance[idx];
-            rad.x += c.x * vis * fp.solarInvPdf;
-            rad.y += c.y * vis * fp.solarInvPdf;
-            rad.z += c.z * vis * fp.solarInvPdf;
-            radiance[idx] = rad;
-            ++rays;
-        }
-    }
+    std::uint32_t nodes = 0, tris = 0, rays = 0;
+    ShadowIO      io{fp, scene, q, radiance, v3(fp.sky.sun_direction)};
+    traceRays<true>(scene.nodes, scene.tris, scene.ordered, *count, fetchCursor, scene.tuning, io, nodes, tris, rays);
     warpStatAdd(&stats[STAT_SHADOW_RAYS], rays);
     warpStatAdd(&stats[STAT_SHADOW_NODES], nodes);
     warpStatAdd(&stats[STAT_SHADOW_TRIS], tris);
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_display(
 
 // ---------------------------------------------------------------------------------------------
 // Scene upload: repack the reference layouts into the traversal layouts (see traversal.cuh).
-__global__ void k_pack_nodes(const rf_bvh_node* __restrict__ src, const std::uint64_t n, float4* dst)
+__global__ void k_pack_nodes(const rf_bvh_node* __restrict__ src, const std::uint64_t n, PackedNode* dst)
 {
     for (std::uint64_t i = blockIdx.x * static_cast<std::uint64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<std::uint64_t>(gridDim.x) * blockDim.x)
@@ -462,8 +465,7 @@ __global__ void k_pack_nodes(const rf_bvh_node* __restrict__ src, const std::uin
         const bool          leaf = s.triangle_count > 0u;
         const std::uint32_t A = leaf ? s.triangles_offset : s.second_child_offset;
         const std::uint32_t B = leaf ? ((s.triangle_count << 2) | 3u) : s.split_axis;
-        dst[2 * i + 0] = make_float4(s.aabb_min[0], s.aabb_min[1], s.aabb_min[2], s.aabb_max[0]);
-        dst[2 * i + 1] = make_float4(s.aabb_max[1], s.aabb_max[2], __uint_as_float(A), __uint_as_float(B));
+        dst[i] = PackedNode{s.aabb_min[0], s.aabb_min[1], s.aabb_min[2], s.aabb_max[0], s.aabb_max[1], s.aabb_max[2], A, B};
     }
 }
 
@@ -485,52 +487,75 @@ __global__ void k_pack_triangles(const float* __restrict__ src, const int stride
 
 // ---------------------------------------------------------------------------------------------
 // bvh-visualizer pixel loop (bvh-visualizer/main.cpp:60-78) and the batched rayIntersectBvh.
-__global__ void __launch_bounds__(BLOCK_THREADS) k_visualizer(
-    const float4* __restrict__ nodes,
+struct VisualizerIO
+{
+    const rf_camera     camera;
+    const std::uint32_t width, height, blocksX;
+    const float         rayTMax;
+    std::uint32_t*      outNodes;
+    // ray i -> pixel: 8x4 pixel blocks (one per 32 consecutive rays), blocks in row-major order
+    __device__ __forceinline__ bool pixel(const std::uint32_t i, std::uint32_t& px, std::uint32_t& py) const
+    {
+        const std::uint32_t block = i >> 5, lane = i & 31u;
+        px = (block % blocksX) * 8u + (lane & 7u);
+        py = (block / blocksX) * 4u + (lane >> 3);
+        return px < width && py < height;
+    }
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
+    {
+        std::uint32_t j, row;
+        if (!pixel(i, j, row)) return false;
+        const float u = __fdiv_rn(static_cast<float>(j), static_cast<float>(width));
+        const float v = 1.0f - __fdiv_rn(static_cast<float>(row + 1u), static_cast<float>(height));
+        // generateCameraRay, camera.cpp:44-51
+        o = v3(camera.origin);
+        d = normalize(((v3(camera.lower_left_corner) + v3(camera.horizontal) * u) + v3(camera.vertical) * v) - o);
+        tmax = rayTMax;
+        return true;
+    }
+    __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord&, const std::uint32_t visited) const
+    {
+        std::uint32_t j, row;
+        pixel(i, j, row);
+        outNodes[row * width + j] = visited;
+    }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer(
+    const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
+    const bool          ordered,
+    const TraceTuning   tuning,
     const rf_camera     camera,
     const std::uint32_t width,
     const std::uint32_t height,
     const float         rayTMax,
+    std::uint32_t*      cursor,
     std::uint32_t*      outNodes)
 {
-    // 8x4 pixel block per warp, blocks in row-major order.
     const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
-    const std::uint32_t totalWarps = blocksX * blocksY;
-    for (std::uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < totalWarps; w += (gridDim.x * blockDim.x) >> 5)
-    {
-        const std::uint32_t j = (w % blocksX) * 8u + (laneId() & 7u);
-        const std::uint32_t i = (w / blocksX) * 4u + (laneId() >> 3);
-        if (j >= width || i >= height) continue;
-        const float u = __fdiv_rn(static_cast<float>(j), static_cast<float>(width));
-        const float v = 1.0f - __fdiv_rn(static_cast<float>(i + 1u), static_cast<float>(height));
-        // generateCameraRay, camera.cpp:44-51.
-        const V3 origin = v3(camera.origin);
-        const V3 dir = normalize(((v3(camera.lower_left_corner) + v3(camera.horizontal) * u) + v3(camera.vertical) * v) - origin);
-        HitRecord     hit;
-        std::uint32_t visited = 0, tested = 0;
-        traverseBvh<false>(nodes, tris, origin, dir, rayTMax, hit, visited, tested);
-        outNodes[i * width + j] = visited;
-    }
+    VisualizerIO        io{camera, width, height, blocksX, rayTMax, outNodes};
+    std::uint32_t       n = 0, t = 0, r = 0;
+    traceRays<false>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io, n, t, r);
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS) k_intersect_batch(
-    const float4* __restrict__ nodes,
-    const float4* __restrict__ tris,
-    const float* __restrict__ rays,
-    const std::uint64_t numRays,
-    const float         rayTMax,
-    std::uint8_t*       outHit,
-    float4*             outPT,
-    std::uint32_t*      outNodes)
+struct BatchIO
 {
-    for (std::uint64_t i = blockIdx.x * static_cast<std::uint64_t>(blockDim.x) + threadIdx.x; i < numRays;
-         i += static_cast<std::uint64_t>(gridDim.x) * blockDim.x)
+    const float*   rays;
+    const float4*  tris;
+    const float    rayTMax;
+    std::uint8_t*  outHit;
+    float4*        outPT;
+    std::uint32_t* outNodes;
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
     {
-        const float*  r = rays + 6 * i;
-        HitRecord     hit;
-        std::uint32_t visited = 0, tested = 0;
-        const bool    didHit = traverseBvh<false>(nodes, tris, v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), rayTMax, hit, visited, tested);
+        const float* r = rays + 6ull * i;
+        o = v3(r[0], r[1], r[2]), d = v3(r[3], r[4], r[5]);
+        tmax = rayTMax;
+        return true;
+    }
+    __device__ __forceinline__ void finish(const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited) const
+    {
         if (outHit) outHit[i] = didHit ? 1 : 0;
         if (outPT)
         {
@@ -544,5 +569,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_intersect_batch(
         }
         if (outNodes) outNodes[i] = visited;
     }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch(
+    const PackedNode* __restrict__ nodes,
+    const float4* __restrict__ tris,
+    const bool          ordered,
+    const TraceTuning   tuning,
+    const float* __restrict__ rays,
+    const std::uint32_t numRays,
+    const float         rayTMax,
+    std::uint32_t*      cursor,
+    std::uint8_t*       outHit,
+    float4*             outPT,
+    std::uint32_t*      outNodes)
+{
+    BatchIO       io{rays, tris, rayTMax, outHit, outPT, outNodes};
+    std::uint32_t n = 0, t = 0, r = 0;
+    traceRays<false>(nodes, tris, ordered, numRays, cursor, tuning, io, n, t, r);
 }
 } // namespace rfb200

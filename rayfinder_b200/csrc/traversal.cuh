@@ -4,18 +4,31 @@
 //   rayIntersectAabb  wgsl:448-475 / ray_intersection.cpp:101-136
 //   rayIntersectTriangle wgsl:478-521 / ray_intersection.cpp:38-90
 //
-// The traversal ORDER and every fp32 operation are those of the reference (strict IEEE, no FMA:
-// this file is compiled with -fmad=false), so nodesVisited is bit-exact and the closest hit — ties
-// included — is the one the reference finds.  What differs is the memory layout the data is pulled
-// through (DESIGN.md "Data layout in HBM"):
+// Per ray, the traversal ORDER and every fp32 operation are those of the reference (strict IEEE, no
+// FMA: this file is compiled with -fmad=false), so nodesVisited is bit-exact and the closest hit — ties
+// included — is the one the reference finds.  What is B200-specific is how a warp is kept busy and how
+// the data is pulled in (DESIGN.md "Traversal kernel"):
 //
-//   node  (32 B = 2 x float4, one 32-byte sector instead of the reference's 48 B / two sectors)
-//         q0 = (min.x, min.y, min.z, max.x)   q1 = (max.y, max.z, A, B)
+//   * persistent warps with per-lane ray refill: a lane whose ray terminates gets the next ray of the
+//     queue (one warp-aggregated atomicAdd), so lanes do not idle until the longest ray of a batch ends;
+//   * node steps and triangle tests are separate phases of one loop: lanes that reached a leaf park
+//     until enough lanes have triangles pending (warp vote), then one triangle round runs for all of
+//     them — the frequent 32-byte node step stays convergent;
+//   * node = 32 B (one sector, ONE LDG.E.256) instead of the reference's 48 B / two sectors:
+//         (min.x, min.y, min.z, max.x, max.y, max.z, A, B)
 //         interior: A = secondChildOffset, B = splitAxis (0..2)
 //         leaf:     A = trianglesOffset,   B = (triangleCount << 2) | 3
-//   tri   (48 B = 3 x float4)  (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, n.xyz)
-//         e1 = v1 - v0, e2 = v2 - v0, n = normalize(cross(e1, e2)) precomputed once at upload with the
-//         same fp32 operations the reference performs per test (so results are unchanged).
+//   * tri  = 48 B (3 x LDG.E.128): (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, n.xyz) with e1 = v1 - v0,
+//     e2 = v2 - v0, n = normalize(cross(e1, e2)) precomputed at upload by the same fp32 operations the
+//     reference performs per test;
+//   * the traversal stack lives in shared memory, one column per thread (bank = lane: conflict-free for
+//     any mix of stack depths), keeping the divergent push/pop traffic out of the L1 tag stage.
+//
+// Slab test: when a ray has finite origin and finite, non-zero 1/direction and the scene's boxes are
+// finite and ordered (checked at upload), no NaN can arise and the reference's sequence of early-outs
+// and std::max/std::min reduces exactly to  max3(lo) <= min3(hi) && max3(lo) < tmax && min3(hi) > 0
+// (proof in DESIGN.md); every other ray takes the literal compare-and-select path, which reproduces the
+// reference's NaN propagation.
 #pragma once
 
 #include "rf_vec.h"
@@ -28,6 +41,14 @@ namespace rfb200
 constexpr float         RF_EPSILON = 0.00001f; // wgsl:66, ray_intersection.cpp:44
 constexpr int           RF_STACK_SIZE = 32;    // wgsl:327,375; ray_intersection.cpp:148
 constexpr std::uint32_t RF_NO_HIT = 0xFFFFFFFFu;
+constexpr int           TRACE_BLOCK_THREADS = 256;
+
+struct __align__(32) PackedNode
+{
+    float         minX, minY, minZ, maxX, maxY, maxZ;
+    std::uint32_t a, b;
+};
+static_assert(sizeof(PackedNode) == 32, "one 32-byte sector per node");
 
 struct HitRecord
 {
@@ -35,7 +56,25 @@ struct HitRecord
     float         u, v, t;
 };
 
+// Scheduling knobs of the persistent loop (tunable at run time, see rf_renderer_set_tuning).
+struct TraceTuning
+{
+    std::uint32_t triMin;    // run a triangle round once this many lanes have a triangle pending
+    std::uint32_t refillMin; // refill once this many lanes are idle
+};
+
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// One 256-bit read-only load (LDG.E.ENL2.256.CONSTANT): the whole node in a single L1 tag lookup.
+__device__ __forceinline__ PackedNode loadNode(const PackedNode* p)
+{
+    PackedNode n;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(n.minX), "=f"(n.minY), "=f"(n.minZ), "=f"(n.maxX), "=f"(n.maxY), "=f"(n.maxZ), "=r"(n.a), "=r"(n.b)
+        : "l"(p));
+    return n;
+}
+__device__ __forceinline__ std::uint32_t laneId() { return threadIdx.x & 31u; }
 
 // One Moeller-Trumbore test against packed triangle `tri`.  Returns true when the reference's
 // rayIntersectTriangle would (det/u/v/t windows identical), with (u, v, t) of the hit.
@@ -78,86 +117,199 @@ __device__ __forceinline__ bool intersectTriangle(
     return false;
 }
 
-// Iterative pre-order traversal with an explicit 32-entry stack.  ANY_HIT = shadowRay semantics
-// (constant rayTMax, return on the first accepted triangle); otherwise closest hit with shrinking
-// tmax.  `nodesVisited` counts loop iterations exactly like ray_intersection.cpp:158.
-template<bool ANY_HIT>
-__device__ __forceinline__ bool traverseBvh(
-    const float4* __restrict__ nodes,
-    const float4* __restrict__ tris,
-    const V3       o,
-    const V3       d,
-    float          tmax,
-    HitRecord&     hit,
-    std::uint32_t& nodesVisited,
-    std::uint32_t& trianglesTested)
+// rayIntersectAabb, literal form: bounds[dirNeg] / bounds[1 - dirNeg] selection, (b - o) * invDir, the
+// two early-outs and std::max/std::min operand order (NaN-propagating) of ray_intersection.cpp:101-136.
+__device__ __forceinline__ bool slabTestExact(
+    const float loX, const float hiX, const float loY, const float hiY, const float loZ, const float hiZ,
+    const V3 o, const float ix, const float iy, const float iz, const float rayTMax)
 {
-    // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
-    const float ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
-    const bool  negX = ix < 0.0f, negY = iy < 0.0f, negZ = iz < 0.0f;
+    float       tmin = (loX - o.x) * ix;
+    float       tmx = (hiX - o.x) * ix;
+    const float tymin = (loY - o.y) * iy;
+    const float tymax = (hiY - o.y) * iy;
+    bool        boxHit = !((tmin > tymax) || (tymin > tmx));
+    tmin = (tymin < tmin) ? tmin : tymin; // std::max(tymin, tmin)
+    tmx = (tmx < tymax) ? tmx : tymax;    // std::min(tymax, tmax)
+    const float tzmin = (loZ - o.z) * iz;
+    const float tzmax = (hiZ - o.z) * iz;
+    boxHit = boxHit && !((tmin > tzmax) || (tzmin > tmx));
+    tmin = (tzmin < tmin) ? tmin : tzmin;
+    tmx = (tmx < tzmax) ? tmx : tzmax;
+    return boxHit && (tmin < rayTMax) && (tmx > 0.0f);
+}
 
-    std::uint32_t stack[RF_STACK_SIZE];
-    int           sp = 0;
-    std::uint32_t cur = 0;
-    bool          didHit = false;
-    hit.tri = RF_NO_HIT;
+// NaN-free form (see the header comment): same products, one 3-way max, one 3-way min, three compares.
+__device__ __forceinline__ bool slabTestFast(
+    const float loX, const float hiX, const float loY, const float hiY, const float loZ, const float hiZ,
+    const V3 o, const float ix, const float iy, const float iz, const float rayTMax)
+{
+    const float txlo = (loX - o.x) * ix, txhi = (hiX - o.x) * ix;
+    const float tylo = (loY - o.y) * iy, tyhi = (hiY - o.y) * iy;
+    const float tzlo = (loZ - o.z) * iz, tzhi = (hiZ - o.z) * iz;
+    const float tmin = fmaxf(fmaxf(txlo, tylo), tzlo);
+    const float tmx = fminf(fminf(txhi, tyhi), tzhi);
+    return (tmin <= tmx) && (tmin < rayTMax) && (tmx > 0.0f);
+}
+
+__device__ __forceinline__ bool isFiniteBits(const float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
+
+// The persistent traversal loop.  IO supplies the rays and consumes the results:
+//   bool IO::fetch(i, o, d, tmax)                              load ray i (false = skip, nothing to trace)
+//   void IO::finish(i, didHit, hit, nodesVisited)              ray i is done
+// ANY_HIT = shadowRay semantics (constant rayTMax, terminate on the first accepted triangle); otherwise
+// closest hit with shrinking tmax.  `sceneOrdered` = the upload-time check that every box is finite with
+// min <= max.  Work is pulled from `*cursor` until `numRays` are consumed.
+template<bool ANY_HIT, class IO>
+__device__ __forceinline__ void traceRays(
+    const PackedNode* __restrict__ nodes,
+    const float4* __restrict__ tris,
+    const bool          sceneOrdered,
+    const std::uint32_t numRays,
+    std::uint32_t*      cursor,
+    const TraceTuning   tuning,
+    IO&                 io,
+    std::uint32_t&      totalNodes,
+    std::uint32_t&      totalTris,
+    std::uint32_t&      totalRays)
+{
+    // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array.
+    __shared__ std::uint32_t stackMem[RF_STACK_SIZE * TRACE_BLOCK_THREADS];
+    std::uint32_t* const     stack = stackMem + threadIdx.x;
+
+    enum : int
+    {
+        IDLE = 0,
+        NODE = 1,
+        TRI = 2
+    };
+    int           state = IDLE;
+    std::uint32_t rayIdx = 0;
+    V3            o = v3(0.f, 0.f, 0.f), d = o;
+    float         ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
+    bool          negX = false, negY = false, negZ = false, exact = false;
+    std::uint32_t cur = 0, sp = 0, pendTri = 0, pendEnd = 0, rayNodes = 0;
+    HitRecord     hit{RF_NO_HIT, 0.f, 0.f, 0.f};
+    bool          exhausted = false;
 
     while (true)
     {
-        ++nodesVisited;
-        const float4 q0 = ldg4(nodes + 2 * cur);
-        const float4 q1 = ldg4(nodes + 2 * cur + 1);
-
-        // rayIntersectAabb: bounds[dirNeg] / bounds[1 - dirNeg] selection, (b - o) * invDir, the two
-        // early-outs and std::max/std::min operand order (NaN-propagating) are the reference's.
-        const float loX = negX ? q0.w : q0.x, hiX = negX ? q0.x : q0.w;
-        const float loY = negY ? q1.x : q0.y, hiY = negY ? q0.y : q1.x;
-        const float loZ = negZ ? q1.y : q0.z, hiZ = negZ ? q0.z : q1.y;
-        float       tmin = (loX - o.x) * ix;
-        float       tmx = (hiX - o.x) * ix;
-        const float tymin = (loY - o.y) * iy;
-        const float tymax = (hiY - o.y) * iy;
-        bool        boxHit = !((tmin > tymax) || (tymin > tmx));
-        tmin = (tymin < tmin) ? tmin : tymin; // std::max(tymin, tmin)
-        tmx = (tmx < tymax) ? tmx : tymax;    // std::min(tymax, tmax)
-        const float tzmin = (loZ - o.z) * iz;
-        const float tzmax = (hiZ - o.z) * iz;
-        boxHit = boxHit && !((tmin > tzmax) || (tzmin > tmx));
-        tmin = (tzmin < tmin) ? tmin : tzmin;
-        tmx = (tmx < tzmax) ? tmx : tzmax;
-        boxHit = boxHit && (tmin < tmax) && (tmx > 0.0f);
-
-        const std::uint32_t A = __float_as_uint(q1.z);
-        const std::uint32_t B = __float_as_uint(q1.w);
-
-        if (boxHit && B < 3u)
+        // ---- refill idle lanes with the next rays of the queue ---------------------------------
+        const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, state == IDLE);
+        if (idleMask != 0u && !exhausted && (static_cast<std::uint32_t>(__popc(idleMask)) >= tuning.refillMin || idleMask == 0xFFFFFFFFu))
         {
-            // interior: visit the near child first by the sign of invDir[splitAxis]
-            const bool neg = (B == 0u) ? negX : ((B == 1u) ? negY : negZ);
-            stack[sp++] = neg ? cur + 1u : A;
-            cur = neg ? A : cur + 1u;
-            continue;
-        }
-        if (boxHit)
-        {
-            const std::uint32_t count = B >> 2;
-            for (std::uint32_t k = 0; k < count; ++k)
+            const std::uint32_t want = static_cast<std::uint32_t>(__popc(idleMask));
+            const int           leader = __ffs(idleMask) - 1;
+            std::uint32_t       base = 0;
+            if (static_cast<int>(laneId()) == leader) base = atomicAdd(cursor, want);
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base + want >= numRays) exhausted = true;
+            if (state == IDLE)
             {
-                ++trianglesTested;
-                float u, v, t;
-                if (intersectTriangle(tris, A + k, o, d, tmax, u, v, t))
+                const std::uint32_t i = base + static_cast<std::uint32_t>(__popc(idleMask & ((1u << laneId()) - 1u)));
+                if (i < numRays && io.fetch(i, o, d, tmax))
                 {
-                    if (ANY_HIT) return true;
-                    tmax = t;
-                    didHit = true;
-                    hit.tri = A + k, hit.u = u, hit.v = v, hit.t = t;
+                    rayIdx = i;
+                    // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
+                    ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
+                    negX = ix < 0.0f, negY = iy < 0.0f, negZ = iz < 0.0f;
+                    exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
+                                               isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
+                    cur = 0, sp = 0, rayNodes = 0;
+                    hit.tri = RF_NO_HIT;
+                    state = NODE;
+                    ++totalRays;
                 }
             }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        if (__ballot_sync(0xFFFFFFFFu, state != IDLE) == 0u)
+        {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- node step: one BVH node per lane in NODE state --------------------------------------
+        if (state == NODE)
+        {
+            ++rayNodes;
+            const PackedNode nd = loadNode(nodes + cur);
+            const float      loX = negX ? nd.maxX : nd.minX, hiX = negX ? nd.minX : nd.maxX;
+            const float      loY = negY ? nd.maxY : nd.minY, hiY = negY ? nd.minY : nd.maxY;
+            const float      loZ = negZ ? nd.maxZ : nd.minZ, hiZ = negZ ? nd.minZ : nd.maxZ;
+            bool             boxHit;
+            if (!exact)
+                boxHit = slabTestFast(loX, hiX, loY, hiY, loZ, hiZ, o, ix, iy, iz, tmax);
+            else
+                boxHit = slabTestExact(loX, hiX, loY, hiY, loZ, hiZ, o, ix, iy, iz, tmax);
+
+            if (boxHit && nd.b < 3u)
+            {
+                // interior: near child first by the sign of invDir[splitAxis]; the other one is pushed
+                const bool neg = (nd.b == 0u) ? negX : ((nd.b == 1u) ? negY : negZ);
+                stack[sp * TRACE_BLOCK_THREADS] = neg ? cur + 1u : nd.a;
+                ++sp;
+                cur = neg ? nd.a : cur + 1u;
+            }
+            else if (boxHit)
+            {
+                pendTri = nd.a;
+                pendEnd = nd.a + (nd.b >> 2);
+                state = TRI;
+            }
+            else if (sp != 0u)
+            {
+                --sp;
+                cur = stack[sp * TRACE_BLOCK_THREADS];
+            }
+            else
+            {
+                totalNodes += rayNodes;
+                io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
+                state = IDLE;
+            }
+        }
+
+        // ---- triangle round: one triangle per lane in TRI state, once enough lanes are parked -------
+        const unsigned triMask = __ballot_sync(0xFFFFFFFFu, state == TRI);
+        const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, state == NODE);
+        if (triMask != 0u && (static_cast<std::uint32_t>(__popc(triMask)) >= tuning.triMin || nodeMask == 0u))
+        {
+            if (state == TRI)
+            {
+                ++totalTris;
+                float      u, v, t;
+                const bool accepted = intersectTriangle(tris, pendTri, o, d, tmax, u, v, t);
+                bool       done = false;
+                if (accepted)
+                {
+                    hit.tri = pendTri, hit.u = u, hit.v = v, hit.t = t;
+                    if (ANY_HIT)
+                        done = true; // shadowRay returns on the first accepted triangle (wgsl:340-342)
+                    else
+                        tmax = t;
+                }
+                ++pendTri;
+                if (!done && pendTri == pendEnd)
+                {
+                    if (sp != 0u)
+                    {
+                        --sp;
+                        cur = stack[sp * TRACE_BLOCK_THREADS];
+                        state = NODE;
+                    }
+                    else
+                    {
+                        done = true;
+                    }
+                }
+                if (done)
+                {
+                    totalNodes += rayNodes;
+                    io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
+                    state = IDLE;
+                }
+            }
+        }
     }
-    return didHit;
 }
 
 // offsetRay, wgsl:523-544 / ray_intersection.cpp:17-35.

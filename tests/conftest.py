@@ -23,13 +23,11 @@ def duck_pt():
 
 @pytest.fixture(scope="session")
 def sponza_pt():
-    import _oracle as O
-    import rayfinder_b200 as rf
+    from rayfinder_b200 import assets as rfa
 
-    path = O.ASSETS / "Sponza.pt"
-    if not path.exists():
-        pytest.skip("assets/Sponza.pt not baked (run __graft_entry__.build() where /root/reference is mounted)")
-    return rf.PtFormat.load(path)
+    if rfa.scene_path("Sponza") is None:
+        pytest.skip("assets/Sponza.pt[.xz] not baked (run __graft_entry__.build() where /root/reference is mounted)")
+    return rfa.load_scene("Sponza")
 
 
 @pytest.fixture(scope="session")
