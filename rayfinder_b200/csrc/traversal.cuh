@@ -138,20 +138,19 @@ __device__ __forceinline__ bool slabTestExact(
     return boxHit && (tmin < rayTMax) && (tmx > 0.0f);
 }
 
-// NaN-free form (see the header comment): same products, one 3-way max, one 3-way min, three compares.
-__device__ __forceinline__ bool slabTestFast(
-    const float loX, const float hiX, const float loY, const float hiY, const float loZ, const float hiZ,
-    const V3 o, const float ix, const float iy, const float iz, const float rayTMax)
-{
-    const float txlo = (loX - o.x) * ix, txhi = (hiX - o.x) * ix;
-    const float tylo = (loY - o.y) * iy, tyhi = (hiY - o.y) * iy;
-    const float tzlo = (loZ - o.z) * iz, tzhi = (hiZ - o.z) * iz;
-    const float tmin = fmaxf(fmaxf(txlo, tylo), tzlo);
-    const float tmx = fminf(fminf(txhi, tyhi), tzhi);
-    return (tmin <= tmx) && (tmin < rayTMax) && (tmx > 0.0f);
-}
-
 __device__ __forceinline__ bool isFiniteBits(const float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
+
+// Shared-memory stack accessors on 32-bit shared-window addresses (one STS / LDS each).
+__device__ __forceinline__ void stackStore(const std::uint32_t addr, const std::uint32_t value)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
+}
+__device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
+{
+    std::uint32_t value;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(addr) : "memory");
+    return value;
+}
 
 // The persistent traversal loop.  IO supplies the rays and consumes the results:
 //   bool IO::fetch(i, o, d, tmax)                              load ray i (false = skip, nothing to trace)
@@ -172,9 +171,12 @@ __device__ __forceinline__ void traceRays(
     std::uint32_t&      totalTris,
     std::uint32_t&      totalRays)
 {
-    // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array.
+    // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array (entry k of this thread
+    // lives STACK_STRIDE * k bytes above stackBase; bank = lane for every k).
     __shared__ std::uint32_t stackMem[RF_STACK_SIZE * TRACE_BLOCK_THREADS];
-    std::uint32_t* const     stack = stackMem + threadIdx.x;
+    constexpr std::uint32_t  STACK_STRIDE = TRACE_BLOCK_THREADS * 4u;
+    const std::uint32_t      stackBase = static_cast<std::uint32_t>(__cvta_generic_to_shared(stackMem + threadIdx.x));
+    std::uint32_t            stackTop = stackBase; // address of the next free entry
 
     enum : int
     {
@@ -182,95 +184,89 @@ __device__ __forceinline__ void traceRays(
         NODE = 1,
         TRI = 2
     };
+    constexpr int NODE_STEPS_PER_VOTE = 2;
+
     int           state = IDLE;
     std::uint32_t rayIdx = 0;
     V3            o = v3(0.f, 0.f, 0.f), d = o;
     float         ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
-    bool          negX = false, negY = false, negZ = false, exact = false;
-    std::uint32_t cur = 0, sp = 0, pendTri = 0, pendEnd = 0, rayNodes = 0;
+    std::uint32_t negMask = 0; // bit a = invDir[a] < 0 (dirNeg); bit 3 stays 0
+    bool          exact = false;
+    std::uint32_t cur = 0, pendTri = 0, pendEnd = 0, rayNodes = 0;
     HitRecord     hit{RF_NO_HIT, 0.f, 0.f, 0.f};
     bool          exhausted = false;
 
+    const auto finishRay = [&]() {
+        totalNodes += rayNodes;
+        io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
+        state = IDLE;
+    };
+
+    // One BVH node for a lane in NODE state (one loop iteration of ray_intersection.cpp:156-204).
+    const auto nodeStep = [&]() {
+        ++rayNodes;
+        const PackedNode nd = loadNode(nodes + cur);
+        bool             boxHit;
+        if (!exact)
+        {
+            // NaN-free form: (b - o) * invDir for both planes of each slab; the sign-selected "near" / "far"
+            // products of the reference are their min / max.
+            const float x0 = (nd.minX - o.x) * ix, x1 = (nd.maxX - o.x) * ix;
+            const float y0 = (nd.minY - o.y) * iy, y1 = (nd.maxY - o.y) * iy;
+            const float z0 = (nd.minZ - o.z) * iz, z1 = (nd.maxZ - o.z) * iz;
+            const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+            const float tmx = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+            boxHit = (tmin <= tmx) && (tmin < tmax) && (tmx > 0.0f);
+        }
+        else
+        {
+            const bool  negX = negMask & 1u, negY = negMask & 2u, negZ = negMask & 4u;
+            const float loX = negX ? nd.maxX : nd.minX, hiX = negX ? nd.minX : nd.maxX;
+            const float loY = negY ? nd.maxY : nd.minY, hiY = negY ? nd.minY : nd.maxY;
+            const float loZ = negZ ? nd.maxZ : nd.minZ, hiZ = negZ ? nd.minZ : nd.maxZ;
+            boxHit = slabTestExact(loX, hiX, loY, hiY, loZ, hiZ, o, ix, iy, iz, tmax);
+        }
+
+        const std::uint32_t kind = nd.b & 3u; // 0..2 = interior split axis, 3 = leaf
+        if (boxHit && kind != 3u)
+        {
+            // interior: near child first by the sign of invDir[splitAxis]; the other one is pushed
+            const bool          neg = (negMask >> kind) & 1u;
+            const std::uint32_t next = cur + 1u;
+            stackStore(stackTop, neg ? next : nd.a);
+            stackTop += STACK_STRIDE;
+            cur = neg ? nd.a : next;
+        }
+        else if (boxHit)
+        {
+            pendTri = nd.a;
+            pendEnd = nd.a + (nd.b >> 2);
+            state = TRI;
+        }
+        else if (stackTop != stackBase)
+        {
+            stackTop -= STACK_STRIDE;
+            cur = stackLoad(stackTop);
+        }
+        else
+        {
+            finishRay();
+        }
+    };
+
     while (true)
     {
-        // ---- refill idle lanes with the next rays of the queue ---------------------------------
-        const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, state == IDLE);
-        if (idleMask != 0u && !exhausted && (static_cast<std::uint32_t>(__popc(idleMask)) >= tuning.refillMin || idleMask == 0xFFFFFFFFu))
+        // ---- node steps: one BVH node per lane in NODE state ------------------------------------------
+#pragma unroll
+        for (int k = 0; k < NODE_STEPS_PER_VOTE; ++k)
         {
-            const std::uint32_t want = static_cast<std::uint32_t>(__popc(idleMask));
-            const int           leader = __ffs(idleMask) - 1;
-            std::uint32_t       base = 0;
-            if (static_cast<int>(laneId()) == leader) base = atomicAdd(cursor, want);
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (base + want >= numRays) exhausted = true;
-            if (state == IDLE)
-            {
-                const std::uint32_t i = base + static_cast<std::uint32_t>(__popc(idleMask & ((1u << laneId()) - 1u)));
-                if (i < numRays && io.fetch(i, o, d, tmax))
-                {
-                    rayIdx = i;
-                    // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
-                    ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
-                    negX = ix < 0.0f, negY = iy < 0.0f, negZ = iz < 0.0f;
-                    exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
-                                               isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
-                    cur = 0, sp = 0, rayNodes = 0;
-                    hit.tri = RF_NO_HIT;
-                    state = NODE;
-                    ++totalRays;
-                }
-            }
-        }
-        if (__ballot_sync(0xFFFFFFFFu, state != IDLE) == 0u)
-        {
-            if (exhausted) break;
-            continue;
+            if (state == NODE) nodeStep();
         }
 
-        // ---- node step: one BVH node per lane in NODE state --------------------------------------
-        if (state == NODE)
-        {
-            ++rayNodes;
-            const PackedNode nd = loadNode(nodes + cur);
-            const float      loX = negX ? nd.maxX : nd.minX, hiX = negX ? nd.minX : nd.maxX;
-            const float      loY = negY ? nd.maxY : nd.minY, hiY = negY ? nd.minY : nd.maxY;
-            const float      loZ = negZ ? nd.maxZ : nd.minZ, hiZ = negZ ? nd.minZ : nd.maxZ;
-            bool             boxHit;
-            if (!exact)
-                boxHit = slabTestFast(loX, hiX, loY, hiY, loZ, hiZ, o, ix, iy, iz, tmax);
-            else
-                boxHit = slabTestExact(loX, hiX, loY, hiY, loZ, hiZ, o, ix, iy, iz, tmax);
-
-            if (boxHit && nd.b < 3u)
-            {
-                // interior: near child first by the sign of invDir[splitAxis]; the other one is pushed
-                const bool neg = (nd.b == 0u) ? negX : ((nd.b == 1u) ? negY : negZ);
-                stack[sp * TRACE_BLOCK_THREADS] = neg ? cur + 1u : nd.a;
-                ++sp;
-                cur = neg ? nd.a : cur + 1u;
-            }
-            else if (boxHit)
-            {
-                pendTri = nd.a;
-                pendEnd = nd.a + (nd.b >> 2);
-                state = TRI;
-            }
-            else if (sp != 0u)
-            {
-                --sp;
-                cur = stack[sp * TRACE_BLOCK_THREADS];
-            }
-            else
-            {
-                totalNodes += rayNodes;
-                io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
-                state = IDLE;
-            }
-        }
-
-        // ---- triangle round: one triangle per lane in TRI state, once enough lanes are parked -------
-        const unsigned triMask = __ballot_sync(0xFFFFFFFFu, state == TRI);
         const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, state == NODE);
+        const unsigned triMask = __ballot_sync(0xFFFFFFFFu, state == TRI);
+
+        // ---- triangle round: one triangle per lane in TRI state, once enough lanes are parked -----------
         if (triMask != 0u && (static_cast<std::uint32_t>(__popc(triMask)) >= tuning.triMin || nodeMask == 0u))
         {
             if (state == TRI)
@@ -290,10 +286,10 @@ __device__ __forceinline__ void traceRays(
                 ++pendTri;
                 if (!done && pendTri == pendEnd)
                 {
-                    if (sp != 0u)
+                    if (stackTop != stackBase)
                     {
-                        --sp;
-                        cur = stack[sp * TRACE_BLOCK_THREADS];
+                        stackTop -= STACK_STRIDE;
+                        cur = stackLoad(stackTop);
                         state = NODE;
                     }
                     else
@@ -301,11 +297,44 @@ __device__ __forceinline__ void traceRays(
                         done = true;
                     }
                 }
-                if (done)
+                if (done) finishRay();
+            }
+            continue; // the masks are stale now; vote again after the next node steps
+        }
+
+        // ---- refill idle lanes with the next rays of the queue / terminate ----------------------------
+        const unsigned activeMask = nodeMask | triMask;
+        if (activeMask == 0xFFFFFFFFu) continue;
+        if (exhausted)
+        {
+            if (activeMask == 0u) break;
+            continue;
+        }
+        const std::uint32_t idleCount = 32u - static_cast<std::uint32_t>(__popc(activeMask));
+        if (idleCount >= tuning.refillMin || activeMask == 0u)
+        {
+            const unsigned      idleMask = ~activeMask;
+            const int           leader = __ffs(idleMask) - 1;
+            std::uint32_t       base = 0;
+            if (static_cast<int>(laneId()) == leader) base = atomicAdd(cursor, idleCount);
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base + idleCount >= numRays) exhausted = true;
+            if (state == IDLE)
+            {
+                const std::uint32_t i = base + static_cast<std::uint32_t>(__popc(idleMask & ((1u << laneId()) - 1u)));
+                if (i < numRays && io.fetch(i, o, d, tmax))
                 {
-                    totalNodes += rayNodes;
-                    io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
-                    state = IDLE;
+                    rayIdx = i;
+                    // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
+                    ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
+                    negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
+                    exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
+                                               isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
+                    cur = 0, rayNodes = 0;
+                    stackTop = stackBase;
+                    hit.tri = RF_NO_HIT;
+                    state = NODE;
+                    ++totalRays;
                 }
             }
         }
