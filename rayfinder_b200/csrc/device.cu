@@ -164,6 +164,42 @@ rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std:
 }
 } // namespace
 
+// Compile-time scheduling variants of the traversal kernels, selected per launch (tuning only).
+template<int V>
+void launchClosestV(int grid, cudaStream_t s, const SceneDevice& scene, const PathQueue& in, const std::uint32_t* inCount,
+                    std::uint32_t* cursor, HitRecord* hits, unsigned long long* stats)
+{
+    k_closest<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(scene, in, inCount, cursor, hits, stats);
+}
+template<int V>
+void launchShadowV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& q,
+                   const std::uint32_t* count, std::uint32_t* cursor, float4* radiance, unsigned long long* stats)
+{
+    k_shadow<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, q, count, cursor, radiance, stats);
+}
+#define RF_VARIANT_SWITCH(CALL)                                                                                       \
+    switch (variant & 15)                                                                                             \
+    {                                                                                                                 \
+    case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break;                   \
+    case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break;                   \
+    case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; case 11: CALL(11); break;               \
+    case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; default: CALL(15); break;           \
+    }
+template<typename... Args>
+void launchClosest(int variant, Args&&... args)
+{
+#define RF_CALL(V) launchClosestV<V>(args...)
+    RF_VARIANT_SWITCH(RF_CALL)
+#undef RF_CALL
+}
+template<typename... Args>
+void launchShadow(int variant, Args&&... args)
+{
+#define RF_CALL(V) launchShadowV<V>(args...)
+    RF_VARIANT_SWITCH(RF_CALL)
+#undef RF_CALL
+}
+
 // =================================================================================================
 struct rf_renderer
 {
@@ -315,6 +351,7 @@ struct rf_renderer
         return RF_OK;
     }
 
+    int variant = TRACE_DEFAULT_VARIANT; // scheduling variant of the traversal kernels (traversal.cuh)
     int traceBlocksPerSm = 4; // 256 threads x <=64 registers, 32 KB of shared stack per block
     int gridFor(int blocksPerSm) const { return numSms * blocksPerSm; }
 };
@@ -529,11 +566,11 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             std::uint32_t* outCount = &ctr->queueCount[outQ];
             RF_CUDA(cudaMemsetAsync(outCount, 0, sizeof(std::uint32_t) + 0, s));
             RF_CUDA(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(ctr->fetch), s));
-            k_closest<<<gridTrace, TRACE_BLOCK_THREADS, 0, s>>>(scene, r->queues[in], inCount, &ctr->fetch[0], r->hits.ptr, r->stats.ptr);
+            launchClosest(r->variant, gridTrace, s, scene, r->queues[in], inCount, &ctr->fetch[0], r->hits.ptr, r->stats.ptr);
             RF_CUDA(stageMark());
             k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], inCount, r->hits.ptr, r->queues[outQ], outCount, r->radiance.ptr);
             RF_CUDA(stageMark());
-            k_shadow<<<gridTrace, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[outQ], outCount, &ctr->fetch[2], r->radiance.ptr, r->stats.ptr);
+            launchShadow(r->variant, gridTrace, s, fp, scene, r->queues[outQ], outCount, &ctr->fetch[2], r->radiance.ptr, r->stats.ptr);
             RF_CUDA(stageMark());
         }
         k_accumulate<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, r->ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
@@ -667,7 +704,9 @@ extern "C" rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enable
 extern "C" rf_status rf_renderer_set_tuning(rf_renderer* r, std::uint32_t triMin, std::uint32_t refillMin, std::uint32_t blocksPerSm)
 {
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: null renderer");
-    if (triMin > 32u || refillMin > 32u || blocksPerSm > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
+    if (triMin > 32u || refillMin > 32u || (blocksPerSm & 0xFFu) > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
+    if (blocksPerSm & 0x100u) r->variant = static_cast<int>((blocksPerSm >> 12) & 15u); // experimental: bits 12-15 = kernel variant
+    blocksPerSm &= 0xFFu;
     if (triMin) r->tuning.triMin = triMin;
     if (refillMin) r->tuning.refillMin = refillMin;
     if (blocksPerSm) r->traceBlocksPerSm = static_cast<int>(blocksPerSm);

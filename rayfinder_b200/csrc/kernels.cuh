@@ -199,6 +199,7 @@ struct ClosestIO
     __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord& hit, std::uint32_t) const { hits[i] = hit; }
 };
 
+template<int VARIANT>
 __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_closest(
     const SceneDevice    scene,
     const PathQueue      in,
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_closest(
 {
     std::uint32_t nodes = 0, tris = 0, rays = 0;
     ClosestIO     io{in, hits};
-    traceRays<false>(scene.nodes, scene.tris, scene.ordered, *inCount, fetchCursor, scene.tuning, io, nodes, tris, rays);
+    traceRays<false, VARIANT>(scene.nodes, scene.tris, scene.ordered, *inCount, fetchCursor, scene.tuning, io, nodes, tris, rays);
     warpStatAdd(&stats[STAT_CLOSEST_RAYS], rays);
     warpStatAdd(&stats[STAT_CLOSEST_NODES], nodes);
     warpStatAdd(&stats[STAT_CLOSEST_TRIS], tris);
@@ -384,6 +385,7 @@ struct ShadowIO
     }
 };
 
+template<int VARIANT>
 __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_shadow(
     const FrameParams    fp,
     const SceneDevice    scene,
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_shadow(
 {
     std::uint32_t nodes = 0, tris = 0, rays = 0;
     ShadowIO      io{fp, scene, q, radiance, v3(fp.sky.sun_direction)};
-    traceRays<true>(scene.nodes, scene.tris, scene.ordered, *count, fetchCursor, scene.tuning, io, nodes, tris, rays);
+    traceRays<true, VARIANT>(scene.nodes, scene.tris, scene.ordered, *count, fetchCursor, scene.tuning, io, nodes, tris, rays);
     warpStatAdd(&stats[STAT_SHADOW_RAYS], rays);
     warpStatAdd(&stats[STAT_SHADOW_NODES], nodes);
     warpStatAdd(&stats[STAT_SHADOW_TRIS], tris);
@@ -536,7 +538,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer(
     const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
     VisualizerIO        io{camera, width, height, blocksX, rayTMax, outNodes};
     std::uint32_t       n = 0, t = 0, r = 0;
-    traceRays<false>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io, n, t, r);
+    traceRays<false, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io, n, t, r);
 }
 
 struct BatchIO
@@ -586,6 +588,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch(
 {
     BatchIO       io{rays, tris, rayTMax, outHit, outPT, outNodes};
     std::uint32_t n = 0, t = 0, r = 0;
-    traceRays<false>(nodes, tris, ordered, numRays, cursor, tuning, io, n, t, r);
+    traceRays<false, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, numRays, cursor, tuning, io, n, t, r);
 }
 } // namespace rfb200

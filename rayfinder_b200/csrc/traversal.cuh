@@ -50,7 +50,7 @@ struct __align__(32) PackedNode
 };
 static_assert(sizeof(PackedNode) == 32, "one 32-byte sector per node");
 
-struct HitRecord
+struct __align__(16) HitRecord
 {
     std::uint32_t tri; // RF_NO_HIT on miss
     float         u, v, t;
@@ -119,10 +119,15 @@ __device__ __forceinline__ bool intersectTriangle(
 
 // rayIntersectAabb, literal form: bounds[dirNeg] / bounds[1 - dirNeg] selection, (b - o) * invDir, the
 // two early-outs and std::max/std::min operand order (NaN-propagating) of ray_intersection.cpp:101-136.
-__device__ __forceinline__ bool slabTestExact(
-    const float loX, const float hiX, const float loY, const float hiY, const float loZ, const float hiZ,
-    const V3 o, const float ix, const float iy, const float iz, const float rayTMax)
+// Out of line on purpose: only rays with a zero / non-finite direction component (or scenes with
+// unordered boxes) come here, and the hot loop should not carry this code.
+__device__ __noinline__ bool slabTestExact(
+    const PackedNode nd, const std::uint32_t negMask, const V3 o, const float ix, const float iy, const float iz, const float rayTMax)
 {
+    const bool  negX = negMask & 1u, negY = negMask & 2u, negZ = negMask & 4u;
+    const float loX = negX ? nd.maxX : nd.minX, hiX = negX ? nd.minX : nd.maxX;
+    const float loY = negY ? nd.maxY : nd.minY, hiY = negY ? nd.minY : nd.maxY;
+    const float loZ = negZ ? nd.maxZ : nd.minZ, hiZ = negZ ? nd.minZ : nd.maxZ;
     float       tmin = (loX - o.x) * ix;
     float       tmx = (hiX - o.x) * ix;
     const float tymin = (loY - o.y) * iy;
@@ -158,7 +163,11 @@ __device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
 // ANY_HIT = shadowRay semantics (constant rayTMax, terminate on the first accepted triangle); otherwise
 // closest hit with shrinking tmax.  `sceneOrdered` = the upload-time check that every box is finite with
 // min <= max.  Work is pulled from `*cursor` until `numRays` are consumed.
-template<bool ANY_HIT, class IO>
+// VARIANT (compile-time scheduling variant, selected per launch for tuning; results never depend on it):
+//   bits 0-1: node steps per warp vote minus 1 (1..4)   bit 2: triangle round tests the whole leaf (else one
+//   triangle per round)   bit 3: node step written as branches (else as selects / predication)
+constexpr int TRACE_DEFAULT_VARIANT = 3;
+template<bool ANY_HIT, int VARIANT, class IO>
 __device__ __forceinline__ void traceRays(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
@@ -180,77 +189,125 @@ __device__ __forceinline__ void traceRays(
 
     enum : int
     {
-        IDLE = 0,
-        NODE = 1,
-        TRI = 2
+        IDLE = 0, // no ray
+        NODE = 1, // next action: visit node `cur`
+        TRI = 2,  // parked at a leaf: triangles [pendTri, pendEnd) to test
+        DONE = 3  // traversal finished, result not yet handed to IO
     };
-    constexpr int NODE_STEPS_PER_VOTE = 2;
+    constexpr int  NODE_STEPS_PER_VOTE = (VARIANT & 3) + 1;
+    constexpr bool TRI_WHOLE_LEAF = (VARIANT & 4) != 0;
+    constexpr bool NODE_BRANCHY = (VARIANT & 8) != 0;
 
     int           state = IDLE;
     std::uint32_t rayIdx = 0;
     V3            o = v3(0.f, 0.f, 0.f), d = o;
     float         ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
     std::uint32_t negMask = 0; // bit a = invDir[a] < 0 (dirNeg); bit 3 stays 0
-    bool          exact = false;
     std::uint32_t cur = 0, pendTri = 0, pendEnd = 0, rayNodes = 0;
     HitRecord     hit{RF_NO_HIT, 0.f, 0.f, 0.f};
     bool          exhausted = false;
 
-    const auto finishRay = [&]() {
-        totalNodes += rayNodes;
-        io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
-        state = IDLE;
-    };
-
-    // One BVH node for a lane in NODE state (one loop iteration of ray_intersection.cpp:156-204).
+    // One BVH node for a lane in NODE state (one loop iteration of ray_intersection.cpp:156-204), written
+    // as selects so that it compiles to predicated straight-line code.
     const auto nodeStep = [&]() {
         ++rayNodes;
         const PackedNode nd = loadNode(nodes + cur);
-        bool             boxHit;
-        if (!exact)
-        {
-            // NaN-free form: (b - o) * invDir for both planes of each slab; the sign-selected "near" / "far"
-            // products of the reference are their min / max.
-            const float x0 = (nd.minX - o.x) * ix, x1 = (nd.maxX - o.x) * ix;
-            const float y0 = (nd.minY - o.y) * iy, y1 = (nd.maxY - o.y) * iy;
-            const float z0 = (nd.minZ - o.z) * iz, z1 = (nd.maxZ - o.z) * iz;
-            const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-            const float tmx = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-            boxHit = (tmin <= tmx) && (tmin < tmax) && (tmx > 0.0f);
-        }
-        else
-        {
-            const bool  negX = negMask & 1u, negY = negMask & 2u, negZ = negMask & 4u;
-            const float loX = negX ? nd.maxX : nd.minX, hiX = negX ? nd.minX : nd.maxX;
-            const float loY = negY ? nd.maxY : nd.minY, hiY = negY ? nd.minY : nd.maxY;
-            const float loZ = negZ ? nd.maxZ : nd.minZ, hiZ = negZ ? nd.minZ : nd.maxZ;
-            boxHit = slabTestExact(loX, hiX, loY, hiY, loZ, hiZ, o, ix, iy, iz, tmax);
-        }
+        // NaN-free form of rayIntersectAabb (see the header comment): (b - o) * invDir for both planes of
+        // each slab; the sign-selected "near" / "far" products of the reference are their min / max.
+        const float x0 = (nd.minX - o.x) * ix, x1 = (nd.maxX - o.x) * ix;
+        const float y0 = (nd.minY - o.y) * iy, y1 = (nd.maxY - o.y) * iy;
+        const float z0 = (nd.minZ - o.z) * iz, z1 = (nd.maxZ - o.z) * iz;
+        const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+        const float tmx = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+        const bool  boxHit = (tmin <= tmx) && (tmin < tmax) && (tmx > 0.0f);
 
         const std::uint32_t kind = nd.b & 3u; // 0..2 = interior split axis, 3 = leaf
-        if (boxHit && kind != 3u)
+        // interior: near child first by the sign of invDir[splitAxis]; the other one is pushed
+        const bool          neg = (negMask >> kind) & 1u;
+        const std::uint32_t next = cur + 1u;
+        if (NODE_BRANCHY)
         {
-            // interior: near child first by the sign of invDir[splitAxis]; the other one is pushed
-            const bool          neg = (negMask >> kind) & 1u;
-            const std::uint32_t next = cur + 1u;
-            stackStore(stackTop, neg ? next : nd.a);
-            stackTop += STACK_STRIDE;
-            cur = neg ? nd.a : next;
-        }
-        else if (boxHit)
-        {
-            pendTri = nd.a;
-            pendEnd = nd.a + (nd.b >> 2);
-            state = TRI;
-        }
-        else if (stackTop != stackBase)
-        {
-            stackTop -= STACK_STRIDE;
-            cur = stackLoad(stackTop);
+            if (boxHit && kind != 3u)
+            {
+                stackStore(stackTop, neg ? next : nd.a);
+                stackTop += STACK_STRIDE;
+                cur = neg ? nd.a : next;
+            }
+            else if (boxHit)
+            {
+                pendTri = nd.a;
+                pendEnd = nd.a + (nd.b >> 2);
+                state = TRI;
+            }
+            else if (stackTop != stackBase)
+            {
+                stackTop -= STACK_STRIDE;
+                cur = stackLoad(stackTop);
+            }
+            else
+            {
+                state = DONE;
+            }
         }
         else
         {
-            finishRay();
+            const bool interior = boxHit && kind != 3u;
+            const bool leaf = boxHit && kind == 3u;
+            if (interior)
+            {
+                stackStore(stackTop, neg ? next : nd.a);
+                stackTop += STACK_STRIDE;
+            }
+            const bool pop = !boxHit && stackTop != stackBase;
+            if (pop)
+            {
+                stackTop -= STACK_STRIDE;
+                cur = stackLoad(stackTop);
+            }
+            if (interior) cur = neg ? nd.a : next;
+            if (leaf)
+            {
+                pendTri = nd.a;
+                pendEnd = nd.a + (nd.b >> 2);
+            }
+            state = interior || pop ? NODE : (leaf ? TRI : DONE);
+        }
+    };
+
+    // Whole-ray traversal with the literal (NaN-propagating) slab test; rare path, see the refill section.
+    const auto traceExactRay = [&]() {
+        while (true)
+        {
+            ++rayNodes;
+            const PackedNode nd = loadNode(nodes + cur);
+            const bool       boxHit = slabTestExact(nd, negMask, o, ix, iy, iz, tmax);
+            const std::uint32_t kind = nd.b & 3u;
+            if (boxHit && kind != 3u)
+            {
+                const bool neg = (negMask >> kind) & 1u;
+                stackStore(stackTop, neg ? cur + 1u : nd.a);
+                stackTop += STACK_STRIDE;
+                cur = neg ? nd.a : cur + 1u;
+                continue;
+            }
+            if (boxHit)
+            {
+                const std::uint32_t end = nd.a + (nd.b >> 2);
+                for (std::uint32_t tri = nd.a; tri != end; ++tri)
+                {
+                    ++totalTris;
+                    float u, v, t;
+                    if (intersectTriangle(tris, tri, o, d, tmax, u, v, t))
+                    {
+                        hit.tri = tri, hit.u = u, hit.v = v, hit.t = t;
+                        if (ANY_HIT) return;
+                        tmax = t;
+                    }
+                }
+            }
+            if (stackTop == stackBase) return;
+            stackTop -= STACK_STRIDE;
+            cur = stackLoad(stackTop);
         }
     };
 
@@ -266,45 +323,53 @@ __device__ __forceinline__ void traceRays(
         const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, state == NODE);
         const unsigned triMask = __ballot_sync(0xFFFFFFFFu, state == TRI);
 
-        // ---- triangle round: one triangle per lane in TRI state, once enough lanes are parked -----------
+        // ---- triangle round: once enough lanes are parked, each tests the triangles of its leaf --------
         if (triMask != 0u && (static_cast<std::uint32_t>(__popc(triMask)) >= tuning.triMin || nodeMask == 0u))
         {
             if (state == TRI)
             {
-                ++totalTris;
-                float      u, v, t;
-                const bool accepted = intersectTriangle(tris, pendTri, o, d, tmax, u, v, t);
-                bool       done = false;
-                if (accepted)
+                bool done = false;
+                do
                 {
-                    hit.tri = pendTri, hit.u = u, hit.v = v, hit.t = t;
-                    if (ANY_HIT)
-                        done = true; // shadowRay returns on the first accepted triangle (wgsl:340-342)
-                    else
-                        tmax = t;
-                }
-                ++pendTri;
-                if (!done && pendTri == pendEnd)
+                    ++totalTris;
+                    float u, v, t;
+                    if (intersectTriangle(tris, pendTri, o, d, tmax, u, v, t))
+                    {
+                        hit.tri = pendTri, hit.u = u, hit.v = v, hit.t = t;
+                        if (ANY_HIT)
+                            done = true; // shadowRay returns on the first accepted triangle (wgsl:340-342)
+                        else
+                            tmax = t;
+                    }
+                    ++pendTri;
+                } while (TRI_WHOLE_LEAF && !done && pendTri != pendEnd);
+                if (!done && pendTri != pendEnd)
                 {
-                    if (stackTop != stackBase)
-                    {
-                        stackTop -= STACK_STRIDE;
-                        cur = stackLoad(stackTop);
-                        state = NODE;
-                    }
-                    else
-                    {
-                        done = true;
-                    }
+                    // one triangle per round: stay parked for the next one
                 }
-                if (done) finishRay();
+                else if (!done && stackTop != stackBase)
+                {
+                    stackTop -= STACK_STRIDE;
+                    cur = stackLoad(stackTop);
+                    state = NODE;
+                }
+                else
+                {
+                    state = DONE;
+                }
             }
             continue; // the masks are stale now; vote again after the next node steps
         }
 
-        // ---- refill idle lanes with the next rays of the queue / terminate ----------------------------
+        // ---- hand finished rays to IO, refill idle lanes with the next rays of the queue, terminate ----
         const unsigned activeMask = nodeMask | triMask;
         if (activeMask == 0xFFFFFFFFu) continue;
+        if (state == DONE)
+        {
+            totalNodes += rayNodes;
+            io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
+            state = IDLE;
+        }
         if (exhausted)
         {
             if (activeMask == 0u) break;
@@ -313,9 +378,9 @@ __device__ __forceinline__ void traceRays(
         const std::uint32_t idleCount = 32u - static_cast<std::uint32_t>(__popc(activeMask));
         if (idleCount >= tuning.refillMin || activeMask == 0u)
         {
-            const unsigned      idleMask = ~activeMask;
-            const int           leader = __ffs(idleMask) - 1;
-            std::uint32_t       base = 0;
+            const unsigned idleMask = ~activeMask;
+            const int      leader = __ffs(idleMask) - 1;
+            std::uint32_t  base = 0;
             if (static_cast<int>(laneId()) == leader) base = atomicAdd(cursor, idleCount);
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (base + idleCount >= numRays) exhausted = true;
@@ -328,13 +393,21 @@ __device__ __forceinline__ void traceRays(
                     // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
                     ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
                     negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
-                    exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
-                                               isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
+                    const bool exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
+                                                          isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
                     cur = 0, rayNodes = 0;
                     stackTop = stackBase;
                     hit.tri = RF_NO_HIT;
                     state = NODE;
                     ++totalRays;
+                    if (exact)
+                    {
+                        // Rays whose slab products can be NaN (zero / non-finite direction component, non-finite
+                        // origin, or a scene with unordered boxes) are traced to completion right here with the
+                        // literal test, so the hot loop above never sees them.
+                        traceExactRay();
+                        state = DONE;
+                    }
                 }
             }
         }
