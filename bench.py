@@ -310,9 +310,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         shadow_bytes = 48 * (stats["shadow_nodes_visited"] + stats["shadow_triangles_tested"])
         launches = args.steps * bounces
         achieved = closest_bytes / (stats["device_ms_closest"] * 1e-3) / 1e9 if stats["device_ms_closest"] > 0 else None
+        traffic = None
+        traffic_files = sorted((ROOT / "profiles").glob("r*_k_closest_traffic.json"))
+        if traffic_files:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            traffic = json.loads(traffic_files[-1].read_text()).get("dram_bytes_per_launch_mean")
+        packed = 32 * stats["closest_nodes_visited"] + 48 * stats["closest_triangles_tested"]
         roofline = {
             "bound": "hbm", "kernel": "k_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": None,
+            "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+            "frac_packed_layout": (packed / (stats["device_ms_closest"] * 1e-3) / 1e9 / peak) if achieved else None,
+            "note": ("algorithmic bytes = 48 B per node visit + 48 B per triangle test (SURVEY.md 8(d)); the 28.7 MB "
+                     "node+triangle set is L1/L2-resident, so DRAM traffic is ~1% of the algorithmic bytes and the binding "
+                     "resources are SM issue slots and the L1 tag stage (profiles/)"),
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
             "algorithmic_bytes_per_launch": closest_bytes / launches, "avg_launch_ms": stats["device_ms_closest"] / launches,
             "launches": launches,
