@@ -30,7 +30,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 METRIC = "Mrays/s (Sponza 1080p, 8 bounces)"
 UNIT = "Mrays/s"
 WIDTH, HEIGHT, BOUNCES = 1920, 1080, 8
-KERNELS_PER_STEP = 2 + 3 * BOUNCES  # raygen + (closest, shade, shadow) per bounce + accumulate
+KERNELS_PER_STEP = 3 + 2 * BOUNCES  # raygen + trace + (shade, trace) per bounce + accumulate
 
 
 def parse_args():
@@ -304,30 +304,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if peaks_path.exists():
             peaks = json.loads(peaks_path.read_text())
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: k_closest (rank 0's launches).  Algorithmic bytes: 48 B per node visited +
-        # 48 B per triangle tested.
-        closest_bytes = 48 * (stats["closest_nodes_visited"] + stats["closest_triangles_tested"])
-        shadow_bytes = 48 * (stats["shadow_nodes_visited"] + stats["shadow_triangles_tested"])
-        launches = args.steps * bounces
-        achieved = closest_bytes / (stats["device_ms_closest"] * 1e-3) / 1e9 if stats["device_ms_closest"] > 0 else None
+        # dominant kernel: k_trace (rank 0's launches): closest-hit + shadow rays share the traversal launches.
+        # Algorithmic bytes: 48 B per node visited + 48 B per triangle tested.
+        nodes = stats["closest_nodes_visited"] + stats["shadow_nodes_visited"]
+        tris = stats["closest_triangles_tested"] + stats["shadow_triangles_tested"]
+        trace_bytes = 48 * (nodes + tris)
+        trace_ms = stats["device_ms_trace"]
+        launches = args.steps * (bounces + 1)
+        achieved = trace_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
         traffic = None
-        traffic_files = sorted((ROOT / "profiles").glob("r*_k_closest_traffic.json"))
+        traffic_files = sorted((ROOT / "profiles").glob("r*_k_trace_traffic.json"))
         if traffic_files:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
             traffic = json.loads(traffic_files[-1].read_text()).get("dram_bytes_per_launch_mean")
-        packed = 32 * stats["closest_nodes_visited"] + 48 * stats["closest_triangles_tested"]
+        packed = 32 * nodes + 48 * tris
         roofline = {
-            "bound": "hbm", "kernel": "k_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-            "frac_packed_layout": (packed / (stats["device_ms_closest"] * 1e-3) / 1e9 / peak) if achieved else None,
+            "frac_packed_layout": (packed / (trace_ms * 1e-3) / 1e9 / peak) if achieved else None,
             "note": ("algorithmic bytes = 48 B per node visit + 48 B per triangle test (SURVEY.md 8(d)); the 28.7 MB "
                      "node+triangle set is L1/L2-resident, so DRAM traffic is ~1% of the algorithmic bytes and the binding "
                      "resources are SM issue slots and the L1 tag stage (profiles/)"),
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
-            "algorithmic_bytes_per_launch": closest_bytes / launches, "avg_launch_ms": stats["device_ms_closest"] / launches,
-            "launches": launches,
-            "packed_bytes_per_launch": (32 * stats["closest_nodes_visited"] + 48 * stats["closest_triangles_tested"]) / launches,
-            "stage_ms_per_step": {k: stats[f"device_ms_{k}"] / args.steps for k in ("closest", "shade", "shadow", "other")},
-            "k_shadow_achieved": shadow_bytes / (stats["device_ms_shadow"] * 1e-3) / 1e9 if stats["device_ms_shadow"] > 0 else None,
+            "algorithmic_bytes_per_launch": trace_bytes / launches, "avg_launch_ms": trace_ms / launches,
+            "launches": launches, "packed_bytes_per_launch": packed / launches,
+            "stage_ms_per_step": {k: stats[f"device_ms_{k}"] / args.steps for k in ("trace", "shade", "other")},
             "mean_nodes_per_closest_ray": stats["closest_nodes_visited"] / max(1, stats["closest_rays"]),
             "mean_nodes_per_shadow_ray": stats["shadow_nodes_visited"] / max(1, stats["shadow_rays"]),
         }
@@ -342,7 +342,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "e2e": {"value": rays_total / e2e_seconds / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": w * h * 16, "ms_per_step": 1e3 * e2e_seconds / args.steps},
-            "gpu_launches": args.steps * KERNELS_PER_STEP if bounces == BOUNCES else args.steps * (2 + 3 * bounces),
+            "gpu_launches": args.steps * (3 + 2 * bounces),
             "roofline": roofline,
             "library": {"path": str(capi.LIB_PATH.relative_to(ROOT)), "build": capi.lib().rf_build_info().decode()},
         }

@@ -181,9 +181,8 @@ typedef struct rf_frame_stats
     uint64_t shadow_nodes_visited;
     uint64_t shadow_triangles_tested;
     double   device_ms_total;      /* CUDA-event time of the render passes */
-    double   device_ms_closest;    /* per-stage CUDA-event time, only filled when stage timing is on */
-    double   device_ms_shadow;
-    double   device_ms_shade;
+    double   device_ms_trace;      /* per-stage CUDA-event time, only filled when stage timing is on: the */
+    double   device_ms_shade;      /* traversal launches (closest-hit + shadow rays), shading, the rest   */
     double   device_ms_other;
 } rf_frame_stats;
 

@@ -78,8 +78,7 @@ class FrameStats(C.Structure):
                 ("shadow_rays", C.c_uint64), ("closest_nodes_visited", C.c_uint64),
                 ("closest_triangles_tested", C.c_uint64), ("shadow_nodes_visited", C.c_uint64),
                 ("shadow_triangles_tested", C.c_uint64), ("device_ms_total", C.c_double),
-                ("device_ms_closest", C.c_double), ("device_ms_shadow", C.c_double),
-                ("device_ms_shade", C.c_double), ("device_ms_other", C.c_double)]
+                ("device_ms_trace", C.c_double), ("device_ms_shade", C.c_double), ("device_ms_other", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/rayfinder_b200.h declares.

@@ -159,45 +159,33 @@ rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std:
         return setError(RF_ERROR_INVALID_ARGUMENT, "Framebuffer size %ux%u outside (0, %ux%u].", p.framebuffer_width, p.framebuffer_height, maxW, maxH);
     if (p.sampling_params.num_samples_per_pixel == 0 || p.sampling_params.num_samples_per_pixel > 65536u)
         return setError(RF_ERROR_INVALID_ARGUMENT, "numSamplesPerPixel must be in [1, 65536].");
-    if (p.sampling_params.num_bounces == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "numBounces must be >= 1.");
+    if (p.sampling_params.num_bounces == 0 || p.sampling_params.num_bounces > 1024u)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "numBounces must be in [1, 1024].");
     return RF_OK;
 }
 } // namespace
 
-// Compile-time scheduling variants of the traversal kernels, selected per launch (tuning only).
+// Compile-time scheduling variants of the traversal kernel, selected per launch (tuning only).
 template<int V>
-void launchClosestV(int grid, cudaStream_t s, const SceneDevice& scene, const PathQueue& in, const std::uint32_t* inCount,
-                    std::uint32_t* cursor, HitRecord* hits, unsigned long long* stats)
+void launchTraceV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& closestQueue,
+                  const std::uint32_t* closestCount, HitRecord* hits, const PathQueue& shadowQueue, const std::uint32_t* shadowCount,
+                  float4* radiance, std::uint32_t* cursor, unsigned long long* stats)
 {
-    k_closest<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(scene, in, inCount, cursor, hits, stats);
+    k_trace<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stats);
 }
-template<int V>
-void launchShadowV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& q,
-                   const std::uint32_t* count, std::uint32_t* cursor, float4* radiance, unsigned long long* stats)
+template<typename... Args>
+void launchTrace(int variant, Args&&... args)
 {
-    k_shadow<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, q, count, cursor, radiance, stats);
-}
-#define RF_VARIANT_SWITCH(CALL)                                                                                       \
-    switch (variant & 15)                                                                                             \
-    {                                                                                                                 \
-    case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break;                   \
-    case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break;                   \
-    case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; case 11: CALL(11); break;               \
-    case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; default: CALL(15); break;           \
+    switch (variant & 15)
+    {
+    case 0: launchTraceV<0>(args...); break;
+    case 1: launchTraceV<1>(args...); break;
+    case 2: launchTraceV<2>(args...); break;
+    case 3: launchTraceV<3>(args...); break;
+    case 7: launchTraceV<7>(args...); break;
+    case 11: launchTraceV<11>(args...); break;
+    default: launchTraceV<TRACE_DEFAULT_VARIANT>(args...); break;
     }
-template<typename... Args>
-void launchClosest(int variant, Args&&... args)
-{
-#define RF_CALL(V) launchClosestV<V>(args...)
-    RF_VARIANT_SWITCH(RF_CALL)
-#undef RF_CALL
-}
-template<typename... Args>
-void launchShadow(int variant, Args&&... args)
-{
-#define RF_CALL(V) launchShadowV<V>(args...)
-    RF_VARIANT_SWITCH(RF_CALL)
-#undef RF_CALL
 }
 
 // =================================================================================================
@@ -226,7 +214,7 @@ struct rf_renderer
     DeviceBuffer<float4>        queueMem; // 2 queues x 4 arrays
     DeviceBuffer<HitRecord>     hits;
     DeviceBuffer<std::uint32_t> ownedTiles;
-    DeviceBuffer<FrameCounters> counters;
+    DeviceBuffer<std::uint32_t> counters; // see counterSlots()
     DeviceBuffer<unsigned long long> stats;
     DeviceBuffer<std::uint32_t> display;
     PathQueue                   queues[2]{};
@@ -254,7 +242,7 @@ struct rf_renderer
     double              totalMs = 0.0;
     std::uint64_t       frames = 0;
     bool                stageTiming = false;
-    double              msClosest = 0, msShadow = 0, msShade = 0, msOther = 0;
+    double              msTrace = 0, msShade = 0, msOther = 0;
 
     ~rf_renderer()
     {
@@ -288,10 +276,10 @@ struct rf_renderer
             durationsMs.push_back(ms);
             if (durationsMs.size() > 30) durationsMs.pop_front(); // reference_path_tracer.cpp:689-693
             totalMs += ms;
-            if (t.stagesUsed == 3 + 3 * t.bounces)
+            if (t.stagesUsed == 4 + 2 * t.bounces)
             {
-                // stage events: [0] before raygen, [1] after raygen, then (closest, shade, shadow) per bounce,
-                // then after accumulate.
+                // stage events: [0] before raygen, [1] after raygen, then per bounce (after k_trace, after
+                // k_shade), then after the last k_trace, after k_accumulate.
                 const auto span = [&](std::uint32_t a, std::uint32_t b) {
                     float x = 0.f;
                     cudaEventElapsedTime(&x, t.stages[a], t.stages[b]);
@@ -299,13 +287,13 @@ struct rf_renderer
                 };
                 msOther += span(0, 1);
                 std::uint32_t e = 1;
-                for (std::uint32_t b = 0; b < t.bounces; ++b, e += 3)
+                for (std::uint32_t b = 0; b < t.bounces; ++b, e += 2)
                 {
-                    msClosest += span(e, e + 1);
+                    msTrace += span(e, e + 1);
                     msShade += span(e + 1, e + 2);
-                    msShadow += span(e + 2, e + 3);
                 }
-                msOther += span(e, e + 1);
+                msTrace += span(e, e + 1);
+                msOther += span(e + 1, e + 2);
             }
             t.stagesUsed = 0;
             eventPool.push_back(std::move(t));
@@ -448,7 +436,7 @@ extern "C" rf_status rf_renderer_create(
     RF_CUDA(r->hits.allocate(maxPixels));
     RF_CUDA(r->queueMem.allocate(maxPixels * 8));
     RF_CUDA(r->ownedTiles.allocate(maxTiles));
-    RF_CUDA(r->counters.allocate(1));
+    RF_CUDA(r->counters.allocate(counterSlots(1024)));
     RF_CUDA(r->stats.allocate(STAT_COUNT));
     RF_CUDA(cudaMemset(r->image.ptr, 0, maxPixels * sizeof(float4)));
     RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
@@ -549,30 +537,31 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         // fsMain:45-47: imageBuffer[idx] = vec3(0f) on the first sample (also clears non-owned tiles).
         RF_CUDA(cudaMemsetAsync(r->image.ptr, 0, numPixels * sizeof(float4), s));
     }
-    FrameCounters* ctr = r->counters.ptr;
-    RF_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FrameCounters), s));
+    std::uint32_t* ctr = r->counters.ptr;
+    RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(fp.numBounces) * sizeof(std::uint32_t), s));
+    std::uint32_t* const cursors = ctr + fp.numBounces + 1u;
 
     const int gridLight = r->gridFor(8);
     const int gridTrace = r->gridFor(r->traceBlocksPerSm);
     RF_CUDA(stageMark());
     if (fp.numOwnedTiles > 0)
     {
-        k_raygen<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->ownedTiles.ptr, r->queues[0], ctr, r->radiance.ptr, r->stats.ptr);
+        k_raygen<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->ownedTiles.ptr, r->queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
+        // closest-hit rays of bounce 1
+        launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[0], &ctr[0], r->hits.ptr, r->queues[0], nullptr, r->radiance.ptr, &cursors[0], r->stats.ptr);
         for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
         {
-            const int      in = (bounce - 1) & 1, outQ = bounce & 1;
-            std::uint32_t* inCount = &ctr->queueCount[in];
-            std::uint32_t* outCount = &ctr->queueCount[outQ];
-            RF_CUDA(cudaMemsetAsync(outCount, 0, sizeof(std::uint32_t) + 0, s));
-            RF_CUDA(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(ctr->fetch), s));
-            launchClosest(r->variant, gridTrace, s, scene, r->queues[in], inCount, &ctr->fetch[0], r->hits.ptr, r->stats.ptr);
+            const int in = (bounce - 1) & 1, outQ = bounce & 1;
             RF_CUDA(stageMark());
-            k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], inCount, r->hits.ptr, r->queues[outQ], outCount, r->radiance.ptr);
+            k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], &ctr[bounce - 1], r->hits.ptr, r->queues[outQ], &ctr[bounce], r->radiance.ptr);
             RF_CUDA(stageMark());
-            launchShadow(r->variant, gridTrace, s, fp, scene, r->queues[outQ], outCount, &ctr->fetch[2], r->radiance.ptr, r->stats.ptr);
-            RF_CUDA(stageMark());
+            // shadow rays of this bounce + closest-hit rays of the next one (none after the last bounce)
+            const bool last = bounce == fp.numBounces;
+            launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[outQ], last ? nullptr : &ctr[bounce], r->hits.ptr, r->queues[outQ], &ctr[bounce],
+                        r->radiance.ptr, &cursors[bounce], r->stats.ptr);
         }
+        RF_CUDA(stageMark());
         k_accumulate<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, r->ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
     }
     RF_CUDA(stageMark());
@@ -675,8 +664,7 @@ extern "C" rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out)
     out->shadow_nodes_visited = s[STAT_SHADOW_NODES];
     out->shadow_triangles_tested = s[STAT_SHADOW_TRIS];
     out->device_ms_total = r->totalMs;
-    out->device_ms_closest = r->msClosest;
-    out->device_ms_shadow = r->msShadow;
+    out->device_ms_trace = r->msTrace;
     out->device_ms_shade = r->msShade;
     out->device_ms_other = r->msOther;
     return RF_OK;
@@ -690,7 +678,7 @@ extern "C" rf_status rf_renderer_reset_stats(rf_renderer* r)
     r->drainTimings(true);
     RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
     r->frames = 0;
-    r->totalMs = r->msClosest = r->msShadow = r->msShade = r->msOther = 0.0;
+    r->totalMs = r->msTrace = r->msShade = r->msOther = 0.0;
     return RF_OK;
 }
 

@@ -2,11 +2,11 @@
 // single fragment shader (pt/reference_path_tracer.wgsl); see DESIGN.md for the stage graph.
 //
 //   k_raygen      fsMain:34-55 (pixel mapping, animatedBlueNoise:603-616, generateCameraRay:237-245)
-//   k_closest     rayIntersectBvh:371-429 for every live path (persistent warps, dynamic fetch)
+//   k_trace       rayIntersectBvh:371-429 for every live path and shadowRay:323-368 + the NEE accumulation of
+//                 rayColor:203 for every hit of the previous bounce, in ONE persistent launch
 //   k_shade       rayColor:181-234 minus the two traversals: hit attributes (:393-400), evalTexture
 //                 (:304-307,553-565), sun sample (:288-292), Lambert scatter (:295-301), sky on miss
 //                 (:213-227,248-275); appends surviving paths to the next queue (stream compaction)
-//   k_shadow      shadowRay:323-368 + the NEE accumulation of rayColor:203
 //   k_accumulate  imageBuffer[idx] += rayColor(...) (fsMain:55)
 //   k_display     estimator / acesFilmic / gamma (fsMain:59-63, :278-285)
 #pragma once
@@ -60,12 +60,11 @@ struct SceneDevice
     TraceTuning          tuning;
 };
 
-// Device counters, zeroed at the start of every frame.
-struct FrameCounters
-{
-    std::uint32_t queueCount[2];   // entries in queue A / B (ping-pong)
-    std::uint32_t fetch[4];        // dynamic work-fetch cursors (closest, shade, shadow, spare)
-};
+// Device counters (u32 array, zeroed once at the start of every frame):
+//   [b]                       b = 0..numBounces: entries of the queue produced for bounce b + 1
+//                             ([0] = primary rays from k_raygen, [b] = hits appended by k_shade of bounce b)
+//   [numBounces + 1 + k]      work-fetch cursor of the k-th traversal launch of the frame
+__host__ __device__ inline std::uint32_t counterSlots(std::uint32_t numBounces) { return 2u * numBounces + 4u; }
 
 enum StatSlot
 {
@@ -134,7 +133,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
     const SceneDevice scene,
     const std::uint32_t* __restrict__ ownedTiles,
     PathQueue           out,
-    FrameCounters*      counters,
+    std::uint32_t*      outCount,
     float4*             radiance,
     unsigned long long* stats)
 {
@@ -145,7 +144,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
     {
         std::uint32_t px = 0, py = 0;
         const bool    valid = slot < total && slotToPixel(fp, ownedTiles, slot, px, py);
-        const std::uint32_t dst = warpAppend(&counters->queueCount[0], valid);
+        const std::uint32_t dst = warpAppend(outCount, valid);
         if (!valid) continue;
         ++generated;
 
@@ -180,40 +179,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
         radiance[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     warpStatAdd(&stats[STAT_PATHS], generated);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Closest-hit traversal of queue `in` (count read from device memory): rayIntersectBvh(ray, T_MAX, &hit).
-struct ClosestIO
-{
-    const PathQueue in;
-    HitRecord*      hits;
-    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
-    {
-        const float4 oo = in.originPix[i];
-        const float4 dd = in.direction[i];
-        o = v3(oo.x, oo.y, oo.z), d = v3(dd.x, dd.y, dd.z);
-        tmax = 10000.0f; // T_MAX, wgsl:73
-        return true;
-    }
-    __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord& hit, std::uint32_t) const { hits[i] = hit; }
-};
-
-template<int VARIANT>
-__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_closest(
-    const SceneDevice    scene,
-    const PathQueue      in,
-    const std::uint32_t* __restrict__ inCount,
-    std::uint32_t*       fetchCursor,
-    HitRecord*           hits,
-    unsigned long long*  stats)
-{
-    std::uint32_t nodes = 0, tris = 0, rays = 0;
-    ClosestIO     io{in, hits};
-    traceRays<false, VARIANT>(scene.nodes, scene.tris, scene.ordered, *inCount, fetchCursor, scene.tuning, io, nodes, tris, rays);
-    warpStatAdd(&stats[STAT_CLOSEST_RAYS], rays);
-    warpStatAdd(&stats[STAT_CLOSEST_NODES], nodes);
-    warpStatAdd(&stats[STAT_CLOSEST_TRIS], tris);
 }
 
 // skyRadiance, wgsl:248-275 (miss path; no solar disk term).
@@ -347,18 +312,36 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shadow rays of queue `q` (every entry is a surface hit): direction = per-pixel sun sample,
-// visibility by any-hit traversal, then radiance += contribution * visibility * SOLAR_INV_PDF.
-struct ShadowIO
+// The traversal launch.  Work items [0, numClosest) are closest-hit rays of `closestQueue`
+// (rayIntersectBvh(ray, T_MAX, &hit), wgsl:190), items [numClosest, numClosest + numShadow) are the shadow
+// rays of `shadowQueue` (shadowRay(Ray(p, lightDirection), T_MAX), wgsl:202, whose result is folded into the
+// NEE term of rayColor:203).  After the k_shade of bounce b both the shadow rays of bounce b and the
+// closest-hit rays of bounce b + 1 are known (same queue, different directions), so they share one launch:
+// 9 traversal launches per 8-bounce frame instead of 16, and one kernel tail instead of two.
+struct TraceIO
 {
-    const FrameParams& fp;
-    const SceneDevice& scene;
-    const PathQueue    q;
-    float4*            radiance;
-    const V3           sunDir;
-    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
+    const FrameParams&  fp;
+    const SceneDevice&  scene;
+    const PathQueue     closestQueue;
+    const std::uint32_t numClosest;
+    HitRecord*          hits;
+    const PathQueue     shadowQueue;
+    float4*             radiance;
+    const V3            sunDir;
+    std::uint32_t*      blockStats; // shared: closest {rays, nodes, tris}, shadow {rays, nodes, tris}
+
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax, bool& anyHit) const
     {
-        const float4        oPix = q.originPix[i];
+        tmax = 10000.0f; // T_MAX, wgsl:73
+        anyHit = i >= numClosest;
+        if (!anyHit)
+        {
+            const float4 oo = closestQueue.originPix[i];
+            const float4 dd = closestQueue.direction[i];
+            o = v3(oo.x, oo.y, oo.z), d = v3(dd.x, dd.y, dd.z);
+            return true;
+        }
+        const float4        oPix = shadowQueue.originPix[i - numClosest];
         const std::uint32_t idx = __float_as_uint(oPix.w);
         const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
         const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
@@ -369,14 +352,24 @@ struct ShadowIO
         const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
         o = v3(oPix.x, oPix.y, oPix.z);
         d = onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
-        tmax = 10000.0f;
         return true;
     }
-    __device__ __forceinline__ void finish(const std::uint32_t i, const bool occluded, const HitRecord&, std::uint32_t) const
+    __device__ __forceinline__ void finish(
+        const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited, const std::uint32_t tested, const bool anyHit) const
     {
-        const std::uint32_t idx = __float_as_uint(q.originPix[i].w);
-        const float         vis = occluded ? 0.0f : 1.0f;
-        const float4        c = q.contribution[i];
+        std::uint32_t* st = blockStats + (anyHit ? 3 : 0);
+        atomicAdd(st + 0, 1u);
+        atomicAdd(st + 1, visited);
+        atomicAdd(st + 2, tested);
+        if (!anyHit)
+        {
+            hits[i] = hit;
+            return;
+        }
+        const std::uint32_t j = i - numClosest;
+        const std::uint32_t idx = __float_as_uint(shadowQueue.originPix[j].w);
+        const float         vis = didHit ? 0.0f : 1.0f; // "Returns 1.0 if no forward intersections, 0.0 otherwise"
+        const float4        c = shadowQueue.contribution[j];
         float4              rad = radiance[idx];
         rad.x += c.x * vis * fp.solarInvPdf;
         rad.y += c.y * vis * fp.solarInvPdf;
@@ -386,21 +379,31 @@ struct ShadowIO
 };
 
 template<int VARIANT>
-__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_shadow(
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_trace(
     const FrameParams    fp,
     const SceneDevice    scene,
-    const PathQueue      q,
-    const std::uint32_t* __restrict__ count,
-    std::uint32_t*       fetchCursor,
+    const PathQueue      closestQueue,
+    const std::uint32_t* __restrict__ closestCount, // nullptr: no closest-hit rays in this launch
+    HitRecord*           hits,
+    const PathQueue      shadowQueue,
+    const std::uint32_t* __restrict__ shadowCount,  // nullptr: no shadow rays in this launch
     float4*              radiance,
+    std::uint32_t*       fetchCursor,
     unsigned long long*  stats)
 {
-    std::uint32_t nodes = 0, tris = 0, rays = 0;
-    ShadowIO      io{fp, scene, q, radiance, v3(fp.sky.sun_direction)};
-    traceRays<true, VARIANT>(scene.nodes, scene.tris, scene.ordered, *count, fetchCursor, scene.tuning, io, nodes, tris, rays);
-    warpStatAdd(&stats[STAT_SHADOW_RAYS], rays);
-    warpStatAdd(&stats[STAT_SHADOW_NODES], nodes);
-    warpStatAdd(&stats[STAT_SHADOW_TRIS], tris);
+    __shared__ std::uint32_t blockStats[6];
+    if (threadIdx.x < 6) blockStats[threadIdx.x] = 0u;
+    __syncthreads();
+    const std::uint32_t numClosest = closestCount ? *closestCount : 0u;
+    const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
+    TraceIO             io{fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance, v3(fp.sky.sun_direction), blockStats};
+    traceRays<2, VARIANT>(scene.nodes, scene.tris, scene.ordered, numClosest + numShadow, fetchCursor, scene.tuning, io);
+    __syncthreads();
+    if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
+    {
+        const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};
+        atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(blockStats[threadIdx.x]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -503,7 +506,7 @@ struct VisualizerIO
         py = (block / blocksX) * 4u + (lane >> 3);
         return px < width && py < height;
     }
-    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax, bool&) const
     {
         std::uint32_t j, row;
         if (!pixel(i, j, row)) return false;
@@ -515,7 +518,7 @@ struct VisualizerIO
         tmax = rayTMax;
         return true;
     }
-    __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord&, const std::uint32_t visited) const
+    __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord&, const std::uint32_t visited, std::uint32_t, bool) const
     {
         std::uint32_t j, row;
         pixel(i, j, row);
@@ -537,8 +540,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer(
 {
     const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
     VisualizerIO        io{camera, width, height, blocksX, rayTMax, outNodes};
-    std::uint32_t       n = 0, t = 0, r = 0;
-    traceRays<false, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io, n, t, r);
+    traceRays<0, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io);
 }
 
 struct BatchIO
@@ -549,14 +551,14 @@ struct BatchIO
     std::uint8_t*  outHit;
     float4*        outPT;
     std::uint32_t* outNodes;
-    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax) const
+    __device__ __forceinline__ bool fetch(const std::uint32_t i, V3& o, V3& d, float& tmax, bool&) const
     {
         const float* r = rays + 6ull * i;
         o = v3(r[0], r[1], r[2]), d = v3(r[3], r[4], r[5]);
         tmax = rayTMax;
         return true;
     }
-    __device__ __forceinline__ void finish(const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited) const
+    __device__ __forceinline__ void finish(const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited, std::uint32_t, bool) const
     {
         if (outHit) outHit[i] = didHit ? 1 : 0;
         if (outPT)
@@ -586,8 +588,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch(
     float4*             outPT,
     std::uint32_t*      outNodes)
 {
-    BatchIO       io{rays, tris, rayTMax, outHit, outPT, outNodes};
-    std::uint32_t n = 0, t = 0, r = 0;
-    traceRays<false, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, numRays, cursor, tuning, io, n, t, r);
+    BatchIO io{rays, tris, rayTMax, outHit, outPT, outNodes};
+    traceRays<0, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, numRays, cursor, tuning, io);
 }
 } // namespace rfb200

@@ -158,16 +158,17 @@ __device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
 }
 
 // The persistent traversal loop.  IO supplies the rays and consumes the results:
-//   bool IO::fetch(i, o, d, tmax)                              load ray i (false = skip, nothing to trace)
-//   void IO::finish(i, didHit, hit, nodesVisited)              ray i is done
-// ANY_HIT = shadowRay semantics (constant rayTMax, terminate on the first accepted triangle); otherwise
-// closest hit with shrinking tmax.  `sceneOrdered` = the upload-time check that every box is finite with
+//   bool IO::fetch(i, o, d, tmax, anyHit)                        load ray i (false = skip, nothing to trace)
+//   void IO::finish(i, didHit, hit, nodesVisited, trisTested, anyHit)   ray i is done
+// anyHit = shadowRay semantics (constant rayTMax, terminate on the first accepted triangle); otherwise
+// closest hit with shrinking tmax.  MODE fixes it at compile time (0: closest, 1: any-hit) or leaves it
+// per ray (2: a mixed queue of closest-hit and shadow rays).  `sceneOrdered` = the upload-time check that every box is finite with
 // min <= max.  Work is pulled from `*cursor` until `numRays` are consumed.
 // VARIANT (compile-time scheduling variant, selected per launch for tuning; results never depend on it):
 //   bits 0-1: node steps per warp vote minus 1 (1..4)   bit 2: triangle round tests the whole leaf (else one
 //   triangle per round)   bit 3: node step written as branches (else as selects / predication)
 constexpr int TRACE_DEFAULT_VARIANT = 3;
-template<bool ANY_HIT, int VARIANT, class IO>
+template<int MODE, int VARIANT, class IO>
 __device__ __forceinline__ void traceRays(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
@@ -175,10 +176,7 @@ __device__ __forceinline__ void traceRays(
     const std::uint32_t numRays,
     std::uint32_t*      cursor,
     const TraceTuning   tuning,
-    IO&                 io,
-    std::uint32_t&      totalNodes,
-    std::uint32_t&      totalTris,
-    std::uint32_t&      totalRays)
+    IO&                 io)
 {
     // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array (entry k of this thread
     // lives STACK_STRIDE * k bytes above stackBase; bank = lane for every k).
@@ -203,9 +201,11 @@ __device__ __forceinline__ void traceRays(
     V3            o = v3(0.f, 0.f, 0.f), d = o;
     float         ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
     std::uint32_t negMask = 0; // bit a = invDir[a] < 0 (dirNeg); bit 3 stays 0
-    std::uint32_t cur = 0, pendTri = 0, pendEnd = 0, rayNodes = 0;
+    std::uint32_t cur = 0, pendTri = 0, pendEnd = 0, rayNodes = 0, rayTris = 0;
     HitRecord     hit{RF_NO_HIT, 0.f, 0.f, 0.f};
     bool          exhausted = false;
+    bool          laneAnyHit = false;
+#define RF_ANY_HIT (MODE == 2 ? laneAnyHit : (MODE == 1))
 
     // One BVH node for a lane in NODE state (one loop iteration of ray_intersection.cpp:156-204), written
     // as selects so that it compiles to predicated straight-line code.
@@ -295,12 +295,12 @@ __device__ __forceinline__ void traceRays(
                 const std::uint32_t end = nd.a + (nd.b >> 2);
                 for (std::uint32_t tri = nd.a; tri != end; ++tri)
                 {
-                    ++totalTris;
+                    ++rayTris;
                     float u, v, t;
                     if (intersectTriangle(tris, tri, o, d, tmax, u, v, t))
                     {
                         hit.tri = tri, hit.u = u, hit.v = v, hit.t = t;
-                        if (ANY_HIT) return;
+                        if (RF_ANY_HIT) return;
                         tmax = t;
                     }
                 }
@@ -331,12 +331,12 @@ __device__ __forceinline__ void traceRays(
                 bool done = false;
                 do
                 {
-                    ++totalTris;
+                    ++rayTris;
                     float u, v, t;
                     if (intersectTriangle(tris, pendTri, o, d, tmax, u, v, t))
                     {
                         hit.tri = pendTri, hit.u = u, hit.v = v, hit.t = t;
-                        if (ANY_HIT)
+                        if (RF_ANY_HIT)
                             done = true; // shadowRay returns on the first accepted triangle (wgsl:340-342)
                         else
                             tmax = t;
@@ -366,8 +366,7 @@ __device__ __forceinline__ void traceRays(
         if (activeMask == 0xFFFFFFFFu) continue;
         if (state == DONE)
         {
-            totalNodes += rayNodes;
-            io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes);
+            io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes, rayTris, RF_ANY_HIT);
             state = IDLE;
         }
         if (exhausted)
@@ -387,7 +386,7 @@ __device__ __forceinline__ void traceRays(
             if (state == IDLE)
             {
                 const std::uint32_t i = base + static_cast<std::uint32_t>(__popc(idleMask & ((1u << laneId()) - 1u)));
-                if (i < numRays && io.fetch(i, o, d, tmax))
+                if (i < numRays && io.fetch(i, o, d, tmax, laneAnyHit))
                 {
                     rayIdx = i;
                     // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
@@ -395,11 +394,10 @@ __device__ __forceinline__ void traceRays(
                     negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
                     const bool exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
                                                           isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
-                    cur = 0, rayNodes = 0;
+                    cur = 0, rayNodes = 0, rayTris = 0;
                     stackTop = stackBase;
                     hit.tri = RF_NO_HIT;
                     state = NODE;
-                    ++totalRays;
                     if (exact)
                     {
                         // Rays whose slab products can be NaN (zero / non-finite direction component, non-finite
@@ -412,6 +410,7 @@ __device__ __forceinline__ void traceRays(
             }
         }
     }
+#undef RF_ANY_HIT
 }
 
 // offsetRay, wgsl:523-544 / ray_intersection.cpp:17-35.

@@ -39,7 +39,7 @@ def main():
         rays = s["closest_rays"] + s["shadow_rays"]
         print(f"variant={variant:2d} (steps={(variant & 3) + 1} leaf={(variant >> 2) & 1} branchy={(variant >> 3) & 1}) "
               f"blocks={blocks} tri_min={tri:2d} refill_min={refill:2d}  total={s['device_ms_total'] / frames:7.3f} ms  "
-              f"closest={s['device_ms_closest'] / frames:7.3f} shadow={s['device_ms_shadow'] / frames:7.3f} "
+              f"trace={s['device_ms_trace'] / frames:7.3f} "
               f"shade={s['device_ms_shade'] / frames:6.3f}  Mrays/s={rays / s['device_ms_total'] / 1e3:8.1f}", flush=True)
 
 
