@@ -169,9 +169,10 @@ rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std:
 template<int V>
 void launchTraceV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& closestQueue,
                   const std::uint32_t* closestCount, HitRecord* hits, const PathQueue& shadowQueue, const std::uint32_t* shadowCount,
-                  float4* radiance, std::uint32_t* cursor, unsigned long long* stats)
+                  float4* radiance, const std::uint32_t* order, std::uint32_t* cursor, unsigned long long* stats)
 {
-    k_trace<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stats);
+    k_trace<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, order, cursor,
+                                                     stats);
 }
 template<typename... Args>
 void launchTrace(int variant, Args&&... args)
@@ -215,6 +216,9 @@ struct rf_renderer
     DeviceBuffer<HitRecord>     hits;
     DeviceBuffer<std::uint32_t> ownedTiles;
     DeviceBuffer<std::uint32_t> counters; // see counterSlots()
+    DeviceBuffer<std::uint32_t> sortKeys, sortOrder, sortHistogram, sortOffsets;
+    std::uint32_t               numTriangles = 0;
+    bool                        sortRays = false; // measured: -4 % traversal time, +4 ms of sorting per frame
     DeviceBuffer<unsigned long long> stats;
     DeviceBuffer<std::uint32_t> display;
     PathQueue                   queues[2]{};
@@ -437,6 +441,13 @@ extern "C" rf_status rf_renderer_create(
     RF_CUDA(r->queueMem.allocate(maxPixels * 8));
     RF_CUDA(r->ownedTiles.allocate(maxTiles));
     RF_CUDA(r->counters.allocate(counterSlots(1024)));
+    r->numTriangles = static_cast<std::uint32_t>(numTris);
+    RF_CUDA(r->sortKeys.allocate(maxPixels));
+    RF_CUDA(r->sortOrder.allocate(maxPixels));
+    RF_CUDA(r->sortHistogram.allocate(numTris));
+    RF_CUDA(r->sortOffsets.allocate(numTris));
+    RF_CUDA(cudaMemset(r->sortHistogram.ptr, 0, numTris * sizeof(std::uint32_t)));
+    if (const char* e = std::getenv("RF_SORT_RAYS")) r->sortRays = std::atoi(e) != 0;
     RF_CUDA(r->stats.allocate(STAT_COUNT));
     RF_CUDA(cudaMemset(r->image.ptr, 0, maxPixels * sizeof(float4)));
     RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
@@ -549,17 +560,25 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         k_raygen<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->ownedTiles.ptr, r->queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
         // closest-hit rays of bounce 1
-        launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[0], &ctr[0], r->hits.ptr, r->queues[0], nullptr, r->radiance.ptr, &cursors[0], r->stats.ptr);
+        launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[0], &ctr[0], r->hits.ptr, r->queues[0], nullptr, r->radiance.ptr, nullptr, &cursors[0],
+                    r->stats.ptr);
         for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
         {
             const int in = (bounce - 1) & 1, outQ = bounce & 1;
             RF_CUDA(stageMark());
-            k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], &ctr[bounce - 1], r->hits.ptr, r->queues[outQ], &ctr[bounce], r->radiance.ptr);
+            const bool sort = r->sortRays;
+            k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], &ctr[bounce - 1], r->hits.ptr, r->queues[outQ], &ctr[bounce], r->radiance.ptr,
+                                                         sort ? r->sortKeys.ptr : nullptr, r->sortHistogram.ptr);
+            if (sort)
+            {
+                k_sort_scan<<<1, SCAN_THREADS, 0, s>>>(r->sortHistogram.ptr, r->sortOffsets.ptr, r->numTriangles);
+                k_sort_scatter<<<gridLight, BLOCK_THREADS, 0, s>>>(&ctr[bounce], r->sortKeys.ptr, r->sortOffsets.ptr, r->sortOrder.ptr);
+            }
             RF_CUDA(stageMark());
             // shadow rays of this bounce + closest-hit rays of the next one (none after the last bounce)
             const bool last = bounce == fp.numBounces;
             launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[outQ], last ? nullptr : &ctr[bounce], r->hits.ptr, r->queues[outQ], &ctr[bounce],
-                        r->radiance.ptr, &cursors[bounce], r->stats.ptr);
+                        r->radiance.ptr, sort ? r->sortOrder.ptr : nullptr, &cursors[bounce], r->stats.ptr);
         }
         RF_CUDA(stageMark());
         k_accumulate<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, r->ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
@@ -694,6 +713,7 @@ extern "C" rf_status rf_renderer_set_tuning(rf_renderer* r, std::uint32_t triMin
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: null renderer");
     if (triMin > 32u || refillMin > 32u || (blocksPerSm & 0xFFu) > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
     if (blocksPerSm & 0x100u) r->variant = static_cast<int>((blocksPerSm >> 12) & 15u); // experimental: bits 12-15 = kernel variant
+    if (blocksPerSm & 0x200u) r->sortRays = ((blocksPerSm >> 10) & 1u) != 0u;                  // experimental: bit 10 = sort rays
     blocksPerSm &= 0xFFu;
     if (triMin) r->tuning.triMin = triMin;
     if (refillMin) r->tuning.refillMin = refillMin;

@@ -24,11 +24,12 @@
 //   * the traversal stack lives in shared memory, one column per thread (bank = lane: conflict-free for
 //     any mix of stack depths), keeping the divergent push/pop traffic out of the L1 tag stage.
 //
-// Slab test: when a ray has finite origin and finite, non-zero 1/direction and the scene's boxes are
-// finite and ordered (checked at upload), no NaN can arise and the reference's sequence of early-outs
-// and std::max/std::min reduces exactly to  max3(lo) <= min3(hi) && max3(lo) < tmax && min3(hi) > 0
-// (proof in DESIGN.md); every other ray takes the literal compare-and-select path, which reproduces the
-// reference's NaN propagation.
+// Slab test: when no slab product (b - o) * invDir is NaN and the scene's boxes are finite and ordered
+// (checked at upload), the reference's sequence of early-outs and std::max/std::min reduces exactly to
+//   max3(lo) <= min3(hi) && max3(lo) < tmax && min3(hi) > 0        (proof in DESIGN.md; +-inf are fine).
+// A NaN product (0 * inf) is detected per node with NaN-propagating min/max and that node is re-tested with
+// the literal compare-and-select form, which reproduces the reference's NaN propagation; rays with NaN or
+// infinite direction components or non-finite origins are traced entirely with the literal form.
 #pragma once
 
 #include "rf_vec.h"
@@ -143,6 +144,38 @@ __device__ __noinline__ bool slabTestExact(
     return boxHit && (tmin < rayTMax) && (tmx > 0.0f);
 }
 
+// NaN-propagating min / max (FMNMX.NAN, FMNMX3.NAN) and the unordered compare (FSETP.NAN).
+__device__ __forceinline__ float minNan(const float a, const float b)
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float maxNan(const float a, const float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min3Nan(const float a, const float b, const float c)
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float max3Nan(const float a, const float b, const float c)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ bool eitherNan(const float a, const float b)
+{
+    int p;
+    asm("{ .reg .pred q; setp.nan.f32 q, %1, %2; selp.s32 %0, 1, 0, q; }" : "=r"(p) : "f"(a), "f"(b));
+    return p != 0;
+}
+
 __device__ __forceinline__ bool isFiniteBits(const float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
 
 // Shared-memory stack accessors on 32-bit shared-window addresses (one STS / LDS each).
@@ -158,8 +191,9 @@ __device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
 }
 
 // The persistent traversal loop.  IO supplies the rays and consumes the results:
-//   bool IO::fetch(i, o, d, tmax, anyHit)                        load ray i (false = skip, nothing to trace)
-//   void IO::finish(i, didHit, hit, nodesVisited, trisTested, anyHit)   ray i is done
+//   bool IO::fetch(id, o, d, tmax, anyHit)   load work item `id` (in/out: IO may replace it by its own ray id;
+//                                            false = skip, nothing to trace)
+//   void IO::finish(id, didHit, hit, nodesVisited, trisTested, anyHit)   ray `id` is done
 // anyHit = shadowRay semantics (constant rayTMax, terminate on the first accepted triangle); otherwise
 // closest hit with shrinking tmax.  MODE fixes it at compile time (0: closest, 1: any-hit) or leaves it
 // per ray (2: a mixed queue of closest-hit and shadow rays).  `sceneOrdered` = the upload-time check that every box is finite with
@@ -212,14 +246,18 @@ __device__ __forceinline__ void traceRays(
     const auto nodeStep = [&]() {
         ++rayNodes;
         const PackedNode nd = loadNode(nodes + cur);
-        // NaN-free form of rayIntersectAabb (see the header comment): (b - o) * invDir for both planes of
-        // each slab; the sign-selected "near" / "far" products of the reference are their min / max.
+        // Fast form of rayIntersectAabb (see the header comment): (b - o) * invDir for both planes of each
+        // slab; the sign-selected "near" / "far" products of the reference are their min / max.  min/max are the
+        // NaN-propagating variants, so a NaN product (0 * inf: an axis-parallel ray whose origin lies exactly
+        // on a slab plane) surfaces in tmin/tmx, is caught by one unordered compare, and that node is re-tested
+        // with the literal form.
         const float x0 = (nd.minX - o.x) * ix, x1 = (nd.maxX - o.x) * ix;
         const float y0 = (nd.minY - o.y) * iy, y1 = (nd.maxY - o.y) * iy;
         const float z0 = (nd.minZ - o.z) * iz, z1 = (nd.maxZ - o.z) * iz;
-        const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-        const float tmx = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-        const bool  boxHit = (tmin <= tmx) && (tmin < tmax) && (tmx > 0.0f);
+        const float tmin = max3Nan(minNan(x0, x1), minNan(y0, y1), minNan(z0, z1));
+        const float tmx = min3Nan(maxNan(x0, x1), maxNan(y0, y1), maxNan(z0, z1));
+        bool        boxHit = (tmin <= tmx) && (tmin < tmax) && (tmx > 0.0f);
+        if (eitherNan(tmin, tmx)) boxHit = slabTestExact(nd, negMask, o, ix, iy, iz, tmax);
 
         const std::uint32_t kind = nd.b & 3u; // 0..2 = interior split axis, 3 = leaf
         // interior: near child first by the sign of invDir[splitAxis]; the other one is pushed
@@ -386,14 +424,17 @@ __device__ __forceinline__ void traceRays(
             if (state == IDLE)
             {
                 const std::uint32_t i = base + static_cast<std::uint32_t>(__popc(idleMask & ((1u << laneId()) - 1u)));
-                if (i < numRays && io.fetch(i, o, d, tmax, laneAnyHit))
+                std::uint32_t       id = i; // IO may translate the work-item index into its own ray id
+                if (i < numRays && io.fetch(id, o, d, tmax, laneAnyHit))
                 {
-                    rayIdx = i;
+                    rayIdx = id;
                     // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
                     ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
                     negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
-                    const bool exact = !sceneOrdered || !(isFiniteBits(ix) && isFiniteBits(iy) && isFiniteBits(iz) && isFiniteBits(o.x) &&
-                                                          isFiniteBits(o.y) && isFiniteBits(o.z) && ix != 0.0f && iy != 0.0f && iz != 0.0f);
+                    // +-inf inverse components (axis-parallel rays) stay on the fast path; NaN or zero ones (NaN or
+                    // infinite direction components) and non-finite origins do not.
+                    const bool exact = !sceneOrdered || !(ix == ix && iy == iy && iz == iz && ix != 0.0f && iy != 0.0f && iz != 0.0f &&
+                                                          isFiniteBits(o.x) && isFiniteBits(o.y) && isFiniteBits(o.z));
                     cur = 0, rayNodes = 0, rayTris = 0;
                     stackTop = stackBase;
                     hit.tri = RF_NO_HIT;

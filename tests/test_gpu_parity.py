@@ -82,6 +82,36 @@ def test_ray_intersect_bvh_batch_bit_exact(duck_pt, golden):
         assert np.array_equal(a[0], b[0])
         assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
         assert np.array_equal(a[2], b[2])
+    # NaN hazards: axis-parallel rays whose origin lies exactly on a slab plane of some BVH node (0 * inf = NaN in
+    # the reference's slab products; std::max/std::min operand order decides what survives)
+    nodes = duck_pt.bvh_nodes
+    pick = rng.integers(0, nodes.size, 4000)
+    origin = rng.uniform(lo - 0.5, hi + 0.5, (4000, 3)).astype(np.float32)
+    direction = rng.normal(size=(4000, 3)).astype(np.float32)
+    for k in range(4000):
+        axis = k % 3
+        origin[k, axis] = nodes["aabb_min" if (k // 3) % 2 else "aabb_max"][pick[k]][axis]
+        direction[k, axis] = 0.0 if (k // 6) % 2 else -0.0
+        if k % 5 == 0:  # two zero components, second origin coordinate on a plane of the root box
+            other = (axis + 1) % 3
+            direction[k, other] = 0.0
+            origin[k, other] = nodes["aabb_min"][0][other]
+    hazard = np.concatenate([origin, direction], axis=1)
+    with np.errstate(all="ignore"):
+        a = scene.ray_intersect_bvh(hazard, rf.FLT_MAX)
+        b = O.oracle_intersect(nodes, tris, hazard, rf.FLT_MAX)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    # rays the fast path must not take at all: NaN / inf direction components, non-finite origins
+    weird = rays[:64].copy()
+    weird[0:16, 3] = np.inf
+    weird[16:32, 4] = np.nan
+    weird[32:48, 0] = np.inf
+    weird[48:64, 2] = np.nan
+    with np.errstate(all="ignore"):
+        a = scene.ray_intersect_bvh(weird, 100.0)
+        b = O.oracle_intersect(nodes, tris, weird, 100.0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
     # empty batch
     hit, p_t, visited = scene.ray_intersect_bvh(np.zeros((0, 6), np.float32), 1.0)
     assert hit.size == 0 and visited.size == 0

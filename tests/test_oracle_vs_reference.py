@@ -132,6 +132,13 @@ def test_oracle_matches_reference_on_random_rays(duck_pt):
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     d[:64] = np.eye(3)[rng.integers(0, 3, 64)] * rng.choice([-1.0, 1.0], (64, 1))  # axis-parallel: invDir = +-inf
     rays = np.concatenate([origin, d], axis=1).astype(np.float32)
+    # NaN hazards: zero direction component and the origin exactly on a slab plane of some node (0 * inf)
+    nodes = duck_pt.bvh_nodes
+    pick = rng.integers(0, nodes.size, 3000)
+    for k in range(3000):
+        axis = k % 3
+        rays[100 + k, axis] = nodes["aabb_min" if (k // 3) % 2 else "aabb_max"][pick[k]][axis]
+        rays[100 + k, 3 + axis] = 0.0 if (k // 6) % 2 else -0.0
     for t_max in (rf.FLT_MAX, 1.5):
         a = O.oracle_intersect(duck_pt.bvh_nodes, O.triangles9(duck_pt), rays, t_max)
         b = O.ref_intersect(duck_pt.bvh_nodes, O.triangles9(duck_pt), rays, t_max)
