@@ -166,26 +166,35 @@ rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std:
 } // namespace
 
 // Compile-time scheduling variants of the traversal kernel, selected per launch (tuning only).
-template<int V>
+template<int V, int BLOCK>
 void launchTraceV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& closestQueue,
                   const std::uint32_t* closestCount, HitRecord* hits, const PathQueue& shadowQueue, const std::uint32_t* shadowCount,
-                  float4* radiance, const std::uint32_t* order, std::uint32_t* cursor, unsigned long long* stats)
+                  float4* radiance, std::uint32_t* cursor, unsigned long long* stats)
 {
-    k_trace<V><<<grid, TRACE_BLOCK_THREADS, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, order, cursor,
-                                                     stats);
+    k_trace<V, BLOCK><<<grid, BLOCK, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stats);
 }
 template<typename... Args>
-void launchTrace(int variant, Args&&... args)
+void launchTrace(int variant, int block, Args&&... args)
 {
-    switch (variant & 15)
+    if (block == 64)
     {
-    case 0: launchTraceV<0>(args...); break;
-    case 1: launchTraceV<1>(args...); break;
-    case 2: launchTraceV<2>(args...); break;
-    case 3: launchTraceV<3>(args...); break;
-    case 7: launchTraceV<7>(args...); break;
-    case 11: launchTraceV<11>(args...); break;
-    default: launchTraceV<TRACE_DEFAULT_VARIANT>(args...); break;
+        if ((variant & 15) == 2) launchTraceV<2, 64>(args...);
+        else launchTraceV<TRACE_DEFAULT_VARIANT, 64>(args...);
+    }
+    else if (block == 128)
+    {
+        if ((variant & 15) == 2) launchTraceV<2, 128>(args...);
+        else launchTraceV<TRACE_DEFAULT_VARIANT, 128>(args...);
+    }
+    else
+    {
+        switch (variant & 15)
+        {
+        case 1: launchTraceV<1, 256>(args...); break;
+        case 2: launchTraceV<2, 256>(args...); break;
+        case 11: launchTraceV<11, 256>(args...); break;
+        default: launchTraceV<TRACE_DEFAULT_VARIANT, 256>(args...); break;
+        }
     }
 }
 
@@ -212,17 +221,28 @@ struct rf_renderer
     // frame state
     std::uint32_t               maxW = 0, maxH = 0;
     DeviceBuffer<float4>        image, radiance;
-    DeviceBuffer<float4>        queueMem; // 2 queues x 4 arrays
-    DeviceBuffer<HitRecord>     hits;
-    DeviceBuffer<std::uint32_t> ownedTiles;
-    DeviceBuffer<std::uint32_t> counters; // see counterSlots()
-    DeviceBuffer<std::uint32_t> sortKeys, sortOrder, sortHistogram, sortOffsets;
-    std::uint32_t               numTriangles = 0;
-    bool                        sortRays = false; // measured: -4 % traversal time, +4 ms of sorting per frame
     DeviceBuffer<unsigned long long> stats;
     DeviceBuffer<std::uint32_t> display;
-    PathQueue                   queues[2]{};
-    std::uint64_t               maxPaths = 0;
+
+    // A frame is traced as `numSubFrames` independent sub-frames (the rank's tiles dealt round-robin), each
+    // with its own queues and stream: while one sub-frame's traversal launch drains its longest rays (a
+    // latency-bound tail of ~0.25 ms per launch), the other sub-frame's kernels fill the machine.
+    struct SubFrame
+    {
+        cudaStream_t                stream = nullptr; // sub-frame 0 runs on the renderer's stream
+        cudaEvent_t                 done = nullptr;
+        DeviceBuffer<float4>        queueMem; // 2 queues x 4 arrays x capacity
+        DeviceBuffer<HitRecord>     hits;
+        DeviceBuffer<std::uint32_t> ownedTiles;
+        DeviceBuffer<std::uint32_t> counters; // see counterSlots()
+        PathQueue                   queues[2]{};
+        std::uint64_t               capacity = 0; // paths
+        std::uint32_t               numOwnedTiles = 0;
+    };
+    static constexpr int MAX_SUBFRAMES = 4;
+    SubFrame    sub[MAX_SUBFRAMES];
+    int         numSubFrames = 2;
+    cudaEvent_t forkEvent = nullptr;
 
     rf_render_parameters params{};
     rf_sky_state         skyState{};
@@ -230,7 +250,7 @@ struct rf_renderer
     std::uint32_t        frameCount = 0;
     std::uint32_t        accumulated = 0;
     std::uint32_t        rank = 0, world = 1;
-    std::uint32_t        numOwnedTiles = 0, tilesX = 0;
+    std::uint32_t        tilesX = 0;
     bool                 tilesDirty = true;
 
     // timing
@@ -259,6 +279,12 @@ struct rf_renderer
         };
         for (auto& t : eventPool) destroy(t);
         for (auto& t : pending) destroy(t);
+        for (auto& sf : sub)
+        {
+            if (sf.stream) cudaStreamDestroy(sf.stream);
+            if (sf.done) cudaEventDestroy(sf.done);
+        }
+        if (forkEvent) cudaEventDestroy(forkEvent);
     }
 
     void drainTimings(bool wait)
@@ -307,9 +333,9 @@ struct rf_renderer
 
     rf_status applyParams(const rf_render_parameters& p)
     {
+        if (p.framebuffer_width != params.framebuffer_width || p.framebuffer_height != params.framebuffer_height) tilesDirty = true;
         params = p;
         accumulated = 0; // reset the temporal accumulation (reference_path_tracer.cpp:561)
-        tilesDirty = true;
         const rf_status st = rf_sky_state_new(&p.sky, &skyState);
         if (st != RF_OK) return st;
         // Sampling tables for every n = frameCount % numSamplesPerPixel.
@@ -331,20 +357,41 @@ struct rf_renderer
         if (!tilesDirty) return RF_OK;
         tilesX = (params.framebuffer_width + TILE - 1) / TILE;
         const std::uint32_t tilesY = (params.framebuffer_height + TILE - 1) / TILE;
-        std::vector<std::uint32_t> owned;
+        std::vector<std::uint32_t> owned[MAX_SUBFRAMES];
+        std::uint32_t              k = 0;
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
-                if ((tx + ty) % world == rank) owned.push_back(ty * tilesX + tx);
-        numOwnedTiles = static_cast<std::uint32_t>(owned.size());
+                if ((tx + ty) % world == rank) owned[k++ % static_cast<std::uint32_t>(numSubFrames)].push_back(ty * tilesX + tx);
         RF_CUDA(cudaStreamSynchronize(stream));
-        if (!owned.empty())
-            RF_CUDA(cudaMemcpy(ownedTiles.ptr, owned.data(), owned.size() * sizeof(std::uint32_t), cudaMemcpyHostToDevice));
+        for (int i = 0; i < MAX_SUBFRAMES; ++i)
+        {
+            SubFrame& sf = sub[i];
+            if (sf.stream) RF_CUDA(cudaStreamSynchronize(sf.stream));
+            sf.numOwnedTiles = i < numSubFrames ? static_cast<std::uint32_t>(owned[i].size()) : 0u;
+            if (sf.numOwnedTiles == 0) continue;
+            const std::uint64_t need = static_cast<std::uint64_t>(sf.numOwnedTiles) * TILE_PIXELS;
+            if (need > sf.capacity)
+            {
+                RF_CUDA(sf.queueMem.allocate(need * 8));
+                RF_CUDA(sf.hits.allocate(need));
+                RF_CUDA(sf.ownedTiles.allocate(sf.numOwnedTiles));
+                if (!sf.counters.ptr) RF_CUDA(sf.counters.allocate(counterSlots(1024)));
+                for (int q = 0; q < 2; ++q)
+                {
+                    float4* base = sf.queueMem.ptr + static_cast<std::uint64_t>(q) * 4 * need;
+                    sf.queues[q] = PathQueue{base, base + need, base + 2 * need, base + 3 * need};
+                }
+                sf.capacity = need;
+            }
+            RF_CUDA(cudaMemcpy(sf.ownedTiles.ptr, owned[i].data(), owned[i].size() * sizeof(std::uint32_t), cudaMemcpyHostToDevice));
+        }
         tilesDirty = false;
         return RF_OK;
     }
 
     int variant = TRACE_DEFAULT_VARIANT; // scheduling variant of the traversal kernels (traversal.cuh)
-    int traceBlocksPerSm = 4; // 256 threads x <=64 registers, 32 KB of shared stack per block
+    int traceBlocksPerSm = 4; // in units of 256 threads: x <= 64 registers, 32 KB of shared stack
+    int traceBlock = 256;     // threads per traversal block (64, 128 or 256)
     int gridFor(int blocksPerSm) const { return numSms * blocksPerSm; }
 };
 
@@ -433,29 +480,20 @@ extern "C" rf_status rf_renderer_create(
     r->maxH = static_cast<std::uint32_t>(desc->max_framebuffer_height);
     const std::uint64_t maxPixels = static_cast<std::uint64_t>(r->maxW) * r->maxH;
     const std::uint64_t maxTiles = static_cast<std::uint64_t>((r->maxW + TILE - 1) / TILE) * ((r->maxH + TILE - 1) / TILE);
-    r->maxPaths = maxPixels;
+    (void)maxTiles;
     RF_CUDA(r->image.allocate(maxPixels));
     RF_CUDA(r->radiance.allocate(maxPixels));
     RF_CUDA(r->display.allocate(maxPixels));
-    RF_CUDA(r->hits.allocate(maxPixels));
-    RF_CUDA(r->queueMem.allocate(maxPixels * 8));
-    RF_CUDA(r->ownedTiles.allocate(maxTiles));
-    RF_CUDA(r->counters.allocate(counterSlots(1024)));
-    r->numTriangles = static_cast<std::uint32_t>(numTris);
-    RF_CUDA(r->sortKeys.allocate(maxPixels));
-    RF_CUDA(r->sortOrder.allocate(maxPixels));
-    RF_CUDA(r->sortHistogram.allocate(numTris));
-    RF_CUDA(r->sortOffsets.allocate(numTris));
-    RF_CUDA(cudaMemset(r->sortHistogram.ptr, 0, numTris * sizeof(std::uint32_t)));
-    if (const char* e = std::getenv("RF_SORT_RAYS")) r->sortRays = std::atoi(e) != 0;
     RF_CUDA(r->stats.allocate(STAT_COUNT));
     RF_CUDA(cudaMemset(r->image.ptr, 0, maxPixels * sizeof(float4)));
     RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
-    for (int q = 0; q < 2; ++q)
+    RF_CUDA(cudaEventCreateWithFlags(&r->forkEvent, cudaEventDisableTiming));
+    for (int i = 0; i < rf_renderer::MAX_SUBFRAMES; ++i)
     {
-        float4* base = r->queueMem.ptr + static_cast<std::uint64_t>(q) * 4 * maxPixels;
-        r->queues[q] = PathQueue{base, base + maxPixels, base + 2 * maxPixels, base + 3 * maxPixels};
+        if (i > 0) RF_CUDA(cudaStreamCreateWithFlags(&r->sub[i].stream, cudaStreamNonBlocking));
+        RF_CUDA(cudaEventCreateWithFlags(&r->sub[i].done, cudaEventDisableTiming));
     }
+    if (const char* e = std::getenv("RF_SUBFRAMES")) r->numSubFrames = std::min(std::max(std::atoi(e), 1), static_cast<int>(rf_renderer::MAX_SUBFRAMES));
 
     st = r->applyParams(desc->render_params);
     if (st != RF_OK) return st;
@@ -503,7 +541,6 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     fp.frameCount = frameCount;
     fp.sampleIndex = frameCount % spp;
     fp.numBounces = r->params.sampling_params.num_bounces;
-    fp.numOwnedTiles = r->numOwnedTiles;
     fp.tilesX = r->tilesX;
     fp.numTextures = r->numTextures;
     fp.numTexels = r->numTexels;
@@ -529,8 +566,10 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     }
     t.stagesUsed = 0;
     t.bounces = fp.numBounces;
+    // Per-stage events are only meaningful when the stages do not overlap: one sub-frame on one stream.
+    const bool staged = r->stageTiming && r->numSubFrames == 1;
     const auto stageMark = [&]() -> cudaError_t {
-        if (!r->stageTiming) return cudaSuccess;
+        if (!staged) return cudaSuccess;
         if (t.stagesUsed >= t.stages.size())
         {
             cudaEvent_t e;
@@ -548,42 +587,47 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         // fsMain:45-47: imageBuffer[idx] = vec3(0f) on the first sample (also clears non-owned tiles).
         RF_CUDA(cudaMemsetAsync(r->image.ptr, 0, numPixels * sizeof(float4), s));
     }
-    std::uint32_t* ctr = r->counters.ptr;
-    RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(fp.numBounces) * sizeof(std::uint32_t), s));
-    std::uint32_t* const cursors = ctr + fp.numBounces + 1u;
+    RF_CUDA(cudaEventRecord(r->forkEvent, s));
 
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->gridFor(r->traceBlocksPerSm);
+    const int gridTrace = r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
     RF_CUDA(stageMark());
-    if (fp.numOwnedTiles > 0)
+    for (int i = 0; i < r->numSubFrames; ++i)
     {
-        k_raygen<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->ownedTiles.ptr, r->queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
+        rf_renderer::SubFrame& sf = r->sub[i];
+        if (sf.numOwnedTiles == 0) continue;
+        cudaStream_t ss = i == 0 ? s : sf.stream;
+        if (i > 0) RF_CUDA(cudaStreamWaitEvent(ss, r->forkEvent, 0));
+        FrameParams sfp = fp;
+        sfp.numOwnedTiles = sf.numOwnedTiles;
+        std::uint32_t* ctr = sf.counters.ptr;
+        RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(fp.numBounces) * sizeof(std::uint32_t), ss));
+        std::uint32_t* const cursors = ctr + fp.numBounces + 1u;
+
+        k_raygen<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
         // closest-hit rays of bounce 1
-        launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[0], &ctr[0], r->hits.ptr, r->queues[0], nullptr, r->radiance.ptr, nullptr, &cursors[0],
-                    r->stats.ptr);
+        launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0], r->stats.ptr);
         for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
         {
             const int in = (bounce - 1) & 1, outQ = bounce & 1;
             RF_CUDA(stageMark());
-            const bool sort = r->sortRays;
-            k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, r->queues[in], &ctr[bounce - 1], r->hits.ptr, r->queues[outQ], &ctr[bounce], r->radiance.ptr,
-                                                         sort ? r->sortKeys.ptr : nullptr, r->sortHistogram.ptr);
-            if (sort)
-            {
-                k_sort_scan<<<1, SCAN_THREADS, 0, s>>>(r->sortHistogram.ptr, r->sortOffsets.ptr, r->numTriangles);
-                k_sort_scatter<<<gridLight, BLOCK_THREADS, 0, s>>>(&ctr[bounce], r->sortKeys.ptr, r->sortOffsets.ptr, r->sortOrder.ptr);
-            }
+            k_shade<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.queues[in], &ctr[bounce - 1], sf.hits.ptr, sf.queues[outQ], &ctr[bounce], r->radiance.ptr);
             RF_CUDA(stageMark());
             // shadow rays of this bounce + closest-hit rays of the next one (none after the last bounce)
             const bool last = bounce == fp.numBounces;
-            launchTrace(r->variant, gridTrace, s, fp, scene, r->queues[outQ], last ? nullptr : &ctr[bounce], r->hits.ptr, r->queues[outQ], &ctr[bounce],
-                        r->radiance.ptr, sort ? r->sortOrder.ptr : nullptr, &cursors[bounce], r->stats.ptr);
+            launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
+                        r->radiance.ptr, &cursors[bounce], r->stats.ptr);
         }
         RF_CUDA(stageMark());
-        k_accumulate<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, r->ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+        k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+        RF_CUDA(stageMark());
+        if (i > 0)
+        {
+            RF_CUDA(cudaEventRecord(sf.done, ss));
+            RF_CUDA(cudaStreamWaitEvent(s, sf.done, 0));
+        }
     }
-    RF_CUDA(stageMark());
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventRecord(t.end, s));
     r->pending.push_back(std::move(t));
@@ -713,7 +757,13 @@ extern "C" rf_status rf_renderer_set_tuning(rf_renderer* r, std::uint32_t triMin
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: null renderer");
     if (triMin > 32u || refillMin > 32u || (blocksPerSm & 0xFFu) > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
     if (blocksPerSm & 0x100u) r->variant = static_cast<int>((blocksPerSm >> 12) & 15u); // experimental: bits 12-15 = kernel variant
-    if (blocksPerSm & 0x200u) r->sortRays = ((blocksPerSm >> 10) & 1u) != 0u;                  // experimental: bit 10 = sort rays
+    if (blocksPerSm & 0x10000u) r->traceBlock = 64 << ((blocksPerSm >> 17) & 3u);               // experimental: bits 17-18 = log2(block / 64)
+    if (r->traceBlock > 256) r->traceBlock = 256;
+    if (blocksPerSm & 0x200u)                                                                  // experimental: bits 10-11 = sub-frames - 1
+    {
+        const int n = static_cast<int>((blocksPerSm >> 10) & 3u) + 1;
+        if (n != r->numSubFrames) r->numSubFrames = n, r->tilesDirty = true;
+    }
     blocksPerSm &= 0xFFu;
     if (triMin) r->tuning.triMin = triMin;
     if (refillMin) r->tuning.refillMin = refillMin;

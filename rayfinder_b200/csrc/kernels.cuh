@@ -211,9 +211,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
     const HitRecord* __restrict__ hits,
     PathQueue            out,
     std::uint32_t*       outCount,
-    float4*              radiance,
-    std::uint32_t*       outKeys,   // per appended entry: the triangle it starts on (sort key), or nullptr
-    std::uint32_t*       histogram) // per triangle: number of appended entries starting on it
+    float4*              radiance)
 {
     const std::uint32_t n = *inCount;
     const std::uint32_t nPadded = (n + 31u) & ~31u;
@@ -306,11 +304,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
         const V3    wi = onbTransform(nrm, v3(cosPhi * hemiSin, sinPhi * hemiSin, __fsqrt_rn(ux)));
         const V3    nextThroughput = throughput * albedo;
 
-        if (outKeys)
-        {
-            outKeys[dst] = hit.tri;
-            atomicAdd(&histogram[hit.tri], 1u);
-        }
         out.originPix[dst] = make_float4(p.x, p.y, p.z, oPix.w);
         out.direction[dst] = make_float4(wi.x, wi.y, wi.z, 0.0f);
         out.throughput[dst] = make_float4(nextThroughput.x, nextThroughput.y, nextThroughput.z, 0.0f);
@@ -336,14 +329,12 @@ struct TraceIO
     float4*             radiance;
     const V3            sunDir;
     std::uint32_t*      blockStats; // shared: closest {rays, nodes, tris}, shadow {rays, nodes, tris}
-    const std::uint32_t* order;     // queue entries in BVH-leaf order of the triangle they start on (or nullptr)
 
     __device__ __forceinline__ bool fetch(std::uint32_t& id, V3& o, V3& d, float& tmax, bool& anyHit) const
     {
         tmax = 10000.0f; // T_MAX, wgsl:73
         anyHit = id >= numClosest;
-        const std::uint32_t slot = anyHit ? id - numClosest : id;
-        id = order ? order[slot] : slot; // the queue entry this work item traces
+        if (anyHit) id -= numClosest; // the queue entry this work item traces
         if (!anyHit)
         {
             const float4 oo = closestQueue.originPix[id];
@@ -388,8 +379,8 @@ struct TraceIO
     }
 };
 
-template<int VARIANT>
-__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_trace(
+template<int VARIANT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_trace(
     const FrameParams    fp,
     const SceneDevice    scene,
     const PathQueue      closestQueue,
@@ -398,7 +389,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_trace(
     const PathQueue      shadowQueue,
     const std::uint32_t* __restrict__ shadowCount,  // nullptr: no shadow rays in this launch
     float4*              radiance,
-    const std::uint32_t* __restrict__ order,
     std::uint32_t*       fetchCursor,
     unsigned long long*  stats)
 {
@@ -407,93 +397,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_trace(
     __syncthreads();
     const std::uint32_t numClosest = closestCount ? *closestCount : 0u;
     const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
-    TraceIO             io{fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance, v3(fp.sky.sun_direction), blockStats, order};
-    traceRays<2, VARIANT>(scene.nodes, scene.tris, scene.ordered, numClosest + numShadow, fetchCursor, scene.tuning, io);
+    TraceIO             io{fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance, v3(fp.sky.sun_direction), blockStats};
+    traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, numClosest + numShadow, fetchCursor, scene.tuning, io);
     __syncthreads();
     if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
     {
         const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};
         atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(blockStats[threadIdx.x]));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Ray reordering between bounces: a counting sort of the queue entries by the triangle they start on.
-// Triangles are stored in BVH leaf order, so consecutive rays of the sorted order start in the same
-// region of the tree: lanes of a warp then walk the same nodes for the first part of their traversal
-// (fewer distinct 128-byte lines per node load, denser triangle rounds).  Results do not depend on the
-// order (every path owns its pixel); k_shade builds the histogram while it appends.
-//   k_sort_scan:    exclusive prefix sum of the histogram (one block), histogram reset to 0
-//   k_sort_scatter: order[offset[key[j]]++] = j
-constexpr int SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(SCAN_THREADS) k_sort_scan(std::uint32_t* histogram, std::uint32_t* offsets, const std::uint32_t numBins)
-{
-    __shared__ std::uint32_t warpSums[32];
-    __shared__ std::uint32_t carry;
-    if (threadIdx.x == 0) carry = 0u;
-    __syncthreads();
-    const std::uint32_t perThread = 8u;
-    const std::uint32_t chunk = SCAN_THREADS * perThread;
-    for (std::uint32_t base = 0; base < numBins; base += chunk)
-    {
-        const std::uint32_t first = base + threadIdx.x * perThread;
-        std::uint32_t       v[8];
-        std::uint32_t       sum = 0;
-#pragma unroll
-        for (std::uint32_t k = 0; k < perThread; ++k)
-        {
-            const std::uint32_t bin = first + k;
-            v[k] = bin < numBins ? histogram[bin] : 0u;
-            if (bin < numBins) histogram[bin] = 0u;
-            sum += v[k];
-        }
-        // block-wide exclusive scan of `sum`
-        std::uint32_t incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const std::uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (static_cast<int>(laneId()) >= d) incl += up;
-        }
-        if (laneId() == 31u) warpSums[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32)
-        {
-            std::uint32_t w = warpSums[threadIdx.x];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const std::uint32_t up = __shfl_up_sync(0xFFFFFFFFu, w, d);
-                if (static_cast<int>(laneId()) >= d) w += up;
-            }
-            warpSums[threadIdx.x] = w; // inclusive over warps
-        }
-        __syncthreads();
-        const std::uint32_t warpBase = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
-        std::uint32_t       running = carry + warpBase + (incl - sum);
-#pragma unroll
-        for (std::uint32_t k = 0; k < perThread; ++k)
-        {
-            const std::uint32_t bin = first + k;
-            if (bin < numBins) offsets[bin] = running;
-            running += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == SCAN_THREADS - 1) carry = running;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(BLOCK_THREADS) k_sort_scatter(
-    const std::uint32_t* __restrict__ count,
-    const std::uint32_t* __restrict__ keys,
-    std::uint32_t*       offsets,
-    std::uint32_t*       order)
-{
-    const std::uint32_t n = *count;
-    for (std::uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-    {
-        order[atomicAdd(&offsets[keys[j]], 1u)] = j;
     }
 }
 
@@ -631,7 +541,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer(
 {
     const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
     VisualizerIO        io{camera, width, height, blocksX, rayTMax, outNodes};
-    traceRays<0, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io);
+    traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io);
 }
 
 struct BatchIO
@@ -680,6 +590,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch(
     std::uint32_t*      outNodes)
 {
     BatchIO io{rays, tris, rayTMax, outHit, outPT, outNodes};
-    traceRays<0, TRACE_DEFAULT_VARIANT>(nodes, tris, ordered, numRays, cursor, tuning, io);
+    traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, numRays, cursor, tuning, io);
 }
 } // namespace rfb200

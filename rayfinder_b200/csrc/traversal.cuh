@@ -202,7 +202,7 @@ __device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
 //   bits 0-1: node steps per warp vote minus 1 (1..4)   bit 2: triangle round tests the whole leaf (else one
 //   triangle per round)   bit 3: node step written as branches (else as selects / predication)
 constexpr int TRACE_DEFAULT_VARIANT = 3;
-template<int MODE, int VARIANT, class IO>
+template<int MODE, int VARIANT, int BLOCK, class IO>
 __device__ __forceinline__ void traceRays(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
@@ -214,8 +214,8 @@ __device__ __forceinline__ void traceRays(
 {
     // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array (entry k of this thread
     // lives STACK_STRIDE * k bytes above stackBase; bank = lane for every k).
-    __shared__ std::uint32_t stackMem[RF_STACK_SIZE * TRACE_BLOCK_THREADS];
-    constexpr std::uint32_t  STACK_STRIDE = TRACE_BLOCK_THREADS * 4u;
+    __shared__ std::uint32_t stackMem[RF_STACK_SIZE * BLOCK];
+    constexpr std::uint32_t  STACK_STRIDE = BLOCK * 4u;
     const std::uint32_t      stackBase = static_cast<std::uint32_t>(__cvta_generic_to_shared(stackMem + threadIdx.x));
     std::uint32_t            stackTop = stackBase; // address of the next free entry
 

@@ -2,7 +2,7 @@
 """Sweep the scheduling knobs of the persistent traversal kernels on one renderer (GPU box).
 Prints one line per setting: per-stage milliseconds of a Sponza 1080p / 8-bounce frame.
 
-    python tools/sweep_tuning.py TRI_LIST REFILL_LIST BLOCKS_LIST VARIANT_LIST SORT_LIST      (comma-separated)
+    python tools/sweep_tuning.py TRI_LIST REFILL_LIST BLOCKS_LIST VARIANT_LIST SUBFRAMES_MINUS_1_LIST      (comma-separated)
 """
 import itertools
 import sys
@@ -20,15 +20,16 @@ def ints(idx, default):
 
 
 def main():
-    w, h, bounces, frames = 1920, 1080, 8, 4
+    import os
+    w, h, bounces, frames = int(os.environ.get('RF_W', 1920)), int(os.environ.get('RF_H', 1080)), 8, 4
     pt = rfa.load_scene("Sponza")
     params = rf.RenderParameters((w, h), rf.fly_camera(w, h), rf.SamplingParams(1, bounces), rf.Sky(), 0.25)
     ren = rf.ReferencePathTracer(params, (w, h), rf.SceneArrays.from_pt(pt))
     ren.set_stage_timing(True)
     tri_list, refill_list = ints(1, "2,4,8"), ints(2, "4")
-    blocks_list, variant_list, sort_list = ints(3, "4"), ints(4, "3"), ints(5, "1")
-    for sort, variant, blocks, tri, refill in itertools.product(sort_list, variant_list, blocks_list, tri_list, refill_list):
-        ren.set_tuning(tri, refill, blocks | 0x100 | (variant << 12) | 0x200 | (sort << 10))
+    blocks_list, variant_list, sort_list, bs_list = ints(3, "4"), ints(4, "3"), ints(5, "1"), ints(6, "256")
+    for bs, sort, variant, blocks, tri, refill in itertools.product(bs_list, sort_list, variant_list, blocks_list, tri_list, refill_list):
+        ren.set_tuning(tri, refill, blocks | 0x100 | (variant << 12) | 0x200 | (sort << 10) | 0x10000 | ({64: 0, 128: 1, 256: 2}[bs] << 17))
         for k in range(frames + 1):
             if k == 1:
                 ren.reset_stats()
@@ -37,7 +38,7 @@ def main():
             ren.render()
         s = ren.stats()
         rays = s["closest_rays"] + s["shadow_rays"]
-        print(f"sort={sort} variant={variant:2d} (steps={(variant & 3) + 1} leaf={(variant >> 2) & 1} branchy={(variant >> 3) & 1}) "
+        print(f"block={bs} subframes={sort + 1} variant={variant:2d} (steps={(variant & 3) + 1} leaf={(variant >> 2) & 1} branchy={(variant >> 3) & 1}) "
               f"blocks={blocks} tri_min={tri:2d} refill_min={refill:2d}  total={s['device_ms_total'] / frames:7.3f} ms  "
               f"trace={s['device_ms_trace'] / frames:7.3f} "
               f"shade={s['device_ms_shade'] / frames:6.3f}  Mrays/s={rays / s['device_ms_total'] / 1e3:8.1f}", flush=True)
