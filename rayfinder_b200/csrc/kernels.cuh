@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
 // NEE term of rayColor:203).  After the k_shade of bounce b both the shadow rays of bounce b and the
 // closest-hit rays of bounce b + 1 are known (same queue, different directions), so they share one launch:
 // 9 traversal launches per 8-bounce frame instead of 16, and one kernel tail instead of two.
-struct TraceIO
+struct TraceIO : CursorSource
 {
     const FrameParams&  fp;
     const SceneDevice&  scene;
@@ -355,8 +355,9 @@ struct TraceIO
         d = onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
         return true;
     }
-    __device__ __forceinline__ void finish(
-        const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited, const std::uint32_t tested, const bool anyHit) const
+    __device__ __forceinline__ bool finish(
+        const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited, const std::uint32_t tested, const bool anyHit,
+        V3&, V3&, float&, bool&) const
     {
         std::uint32_t* st = blockStats + (anyHit ? 3 : 0);
         atomicAdd(st + 0, 1u);
@@ -365,7 +366,7 @@ struct TraceIO
         if (!anyHit)
         {
             hits[i] = hit;
-            return;
+            return false;
         }
         const std::uint32_t j = i;
         const std::uint32_t idx = __float_as_uint(shadowQueue.originPix[j].w);
@@ -376,6 +377,7 @@ struct TraceIO
         rad.y += c.y * vis * fp.solarInvPdf;
         rad.z += c.z * vis * fp.solarInvPdf;
         radiance[idx] = rad;
+        return false;
     }
 };
 
@@ -397,8 +399,9 @@ __global__ void __launch_bounds__(BLOCK) k_trace(
     __syncthreads();
     const std::uint32_t numClosest = closestCount ? *closestCount : 0u;
     const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
-    TraceIO             io{fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance, v3(fp.sky.sun_direction), blockStats};
-    traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, numClosest + numShadow, fetchCursor, scene.tuning, io);
+    TraceIO             io{{fetchCursor, numClosest + numShadow}, fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance,
+               v3(fp.sky.sun_direction), blockStats};
+    traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
     __syncthreads();
     if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
     {
@@ -493,7 +496,7 @@ __global__ void k_pack_triangles(const float* __restrict__ src, const int stride
 
 // ---------------------------------------------------------------------------------------------
 // bvh-visualizer pixel loop (bvh-visualizer/main.cpp:60-78) and the batched rayIntersectBvh.
-struct VisualizerIO
+struct VisualizerIO : CursorSource
 {
     const rf_camera     camera;
     const std::uint32_t width, height, blocksX;
@@ -519,11 +522,12 @@ struct VisualizerIO
         tmax = rayTMax;
         return true;
     }
-    __device__ __forceinline__ void finish(const std::uint32_t i, bool, const HitRecord&, const std::uint32_t visited, std::uint32_t, bool) const
+    __device__ __forceinline__ bool finish(const std::uint32_t i, bool, const HitRecord&, const std::uint32_t visited, std::uint32_t, bool, V3&, V3&, float&, bool&) const
     {
         std::uint32_t j, row;
         pixel(i, j, row);
         outNodes[row * width + j] = visited;
+        return false;
     }
 };
 
@@ -540,11 +544,11 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer(
     std::uint32_t*      outNodes)
 {
     const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
-    VisualizerIO        io{camera, width, height, blocksX, rayTMax, outNodes};
-    traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, blocksX * blocksY * 32u, cursor, tuning, io);
+    VisualizerIO        io{{cursor, blocksX * blocksY * 32u}, camera, width, height, blocksX, rayTMax, outNodes};
+    traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, tuning, io);
 }
 
-struct BatchIO
+struct BatchIO : CursorSource
 {
     const float*   rays;
     const float4*  tris;
@@ -559,7 +563,7 @@ struct BatchIO
         tmax = rayTMax;
         return true;
     }
-    __device__ __forceinline__ void finish(const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited, std::uint32_t, bool) const
+    __device__ __forceinline__ bool finish(const std::uint32_t i, const bool didHit, const HitRecord& hit, const std::uint32_t visited, std::uint32_t, bool, V3&, V3&, float&, bool&) const
     {
         if (outHit) outHit[i] = didHit ? 1 : 0;
         if (outPT)
@@ -573,6 +577,7 @@ struct BatchIO
             outPT[i] = pt;
         }
         if (outNodes) outNodes[i] = visited;
+        return false;
     }
 };
 
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch(
     float4*             outPT,
     std::uint32_t*      outNodes)
 {
-    BatchIO io{rays, tris, rayTMax, outHit, outPT, outNodes};
-    traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, numRays, cursor, tuning, io);
+    BatchIO io{{cursor, numRays}, rays, tris, rayTMax, outHit, outPT, outNodes};
+    traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, tuning, io);
 }
 } // namespace rfb200

@@ -57,6 +57,22 @@ struct __align__(16) HitRecord
     float         u, v, t;
 };
 
+// Work source over a plain array of `numRays` items: a device cursor advanced with one atomicAdd per warp.
+struct CursorSource
+{
+    std::uint32_t* cursor;
+    std::uint32_t  numRays;
+    __device__ __forceinline__ std::uint32_t acquire(const std::uint32_t want, bool, std::uint32_t& base, bool& exhausted) const
+    {
+        std::uint32_t b = 0;
+        if ((threadIdx.x & 31u) == 0u) b = atomicAdd(cursor, want);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        base = b;
+        exhausted = b + want >= numRays;
+        return b < numRays ? min(want, numRays - b) : 0u;
+    }
+};
+
 // Scheduling knobs of the persistent loop (tunable at run time, see rf_renderer_set_tuning).
 struct TraceTuning
 {
@@ -191,13 +207,19 @@ __device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
 }
 
 // The persistent traversal loop.  IO supplies the rays and consumes the results:
+//   uint32 IO::acquire(want, mayWait, base, exhausted)   warp-uniform: reserve up to `want` work items, return
+//                                            how many were granted (items base .. base+granted-1); set `exhausted`
+//                                            when no item will ever come again; `mayWait` = the warp has nothing
+//                                            else to do
 //   bool IO::fetch(id, o, d, tmax, anyHit)   load work item `id` (in/out: IO may replace it by its own ray id;
 //                                            false = skip, nothing to trace)
-//   void IO::finish(id, didHit, hit, nodesVisited, trisTested, anyHit)   ray `id` is done
+//   bool IO::finish(id, didHit, hit, nodesVisited, trisTested, anyHit, o, d, tmax, anyHitNext)
+//                                            ray `id` is done; return true to chain another ray on this lane
+//                                            (o, d, tmax, anyHitNext filled in; same id)
 // anyHit = shadowRay semantics (constant rayTMax, terminate on the first accepted triangle); otherwise
 // closest hit with shrinking tmax.  MODE fixes it at compile time (0: closest, 1: any-hit) or leaves it
-// per ray (2: a mixed queue of closest-hit and shadow rays).  `sceneOrdered` = the upload-time check that every box is finite with
-// min <= max.  Work is pulled from `*cursor` until `numRays` are consumed.
+// per ray (2: a mixed stream of closest-hit and shadow rays).  `sceneOrdered` = the upload-time check that
+// every box is finite with min <= max.
 // VARIANT (compile-time scheduling variant, selected per launch for tuning; results never depend on it):
 //   bits 0-1: node steps per warp vote minus 1 (1..4)   bit 2: triangle round tests the whole leaf (else one
 //   triangle per round)   bit 3: node step written as branches (else as selects / predication)
@@ -207,8 +229,6 @@ __device__ __forceinline__ void traceRays(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
     const bool          sceneOrdered,
-    const std::uint32_t numRays,
-    std::uint32_t*      cursor,
     const TraceTuning   tuning,
     IO&                 io)
 {
@@ -349,6 +369,29 @@ __device__ __forceinline__ void traceRays(
         }
     };
 
+    // Set up the traversal of the ray (o, d, tmax) on this lane: rayAabbIntersector, wgsl:438-445 /
+    // ray_intersection.cpp:92-99.
+    const auto startRay = [&]() {
+        ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
+        negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
+        // +-inf inverse components (axis-parallel rays) stay on the fast path; NaN or zero ones (NaN or
+        // infinite direction components) and non-finite origins do not.
+        const bool exact = !sceneOrdered || !(ix == ix && iy == iy && iz == iz && ix != 0.0f && iy != 0.0f && iz != 0.0f &&
+                                              isFiniteBits(o.x) && isFiniteBits(o.y) && isFiniteBits(o.z));
+        cur = 0, rayNodes = 0, rayTris = 0;
+        stackTop = stackBase;
+        hit.tri = RF_NO_HIT;
+        state = NODE;
+        if (exact)
+        {
+            // Rays whose slab products can be NaN in every node (zero / non-finite direction component, non-finite
+            // origin, or a scene with unordered boxes) are traced to completion right here with the literal test,
+            // so the hot loop never sees them.
+            traceExactRay();
+            state = DONE;
+        }
+    };
+
     while (true)
     {
         // ---- node steps: one BVH node per lane in NODE state ------------------------------------------
@@ -399,57 +442,35 @@ __device__ __forceinline__ void traceRays(
             continue; // the masks are stale now; vote again after the next node steps
         }
 
-        // ---- hand finished rays to IO, refill idle lanes with the next rays of the queue, terminate ----
-        const unsigned activeMask = nodeMask | triMask;
-        if (activeMask == 0xFFFFFFFFu) continue;
+        // ---- hand finished rays to IO, refill idle lanes with the next work items, terminate ----------
+        if ((nodeMask | triMask) == 0xFFFFFFFFu) continue;
         if (state == DONE)
         {
-            io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes, rayTris, RF_ANY_HIT);
-            state = IDLE;
+            if (io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes, rayTris, RF_ANY_HIT, o, d, tmax, laneAnyHit))
+                startRay(); // chained ray (e.g. the closest-hit ray of a path right after its shadow ray)
+            else
+                state = IDLE;
         }
-        if (exhausted)
+        const unsigned      busyMask = __ballot_sync(0xFFFFFFFFu, state != IDLE);
+        const std::uint32_t idleCount = 32u - static_cast<std::uint32_t>(__popc(busyMask));
+        bool                gotWork = false;
+        if (!exhausted && idleCount != 0u && (idleCount >= tuning.refillMin || busyMask == 0u))
         {
-            if (activeMask == 0u) break;
-            continue;
-        }
-        const std::uint32_t idleCount = 32u - static_cast<std::uint32_t>(__popc(activeMask));
-        if (idleCount >= tuning.refillMin || activeMask == 0u)
-        {
-            const unsigned idleMask = ~activeMask;
-            const int      leader = __ffs(idleMask) - 1;
-            std::uint32_t  base = 0;
-            if (static_cast<int>(laneId()) == leader) base = atomicAdd(cursor, idleCount);
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (base + idleCount >= numRays) exhausted = true;
+            std::uint32_t       base = 0;
+            const std::uint32_t granted = io.acquire(idleCount, busyMask == 0u, base, exhausted);
+            gotWork = granted != 0u;
             if (state == IDLE)
             {
-                const std::uint32_t i = base + static_cast<std::uint32_t>(__popc(idleMask & ((1u << laneId()) - 1u)));
-                std::uint32_t       id = i; // IO may translate the work-item index into its own ray id
-                if (i < numRays && io.fetch(id, o, d, tmax, laneAnyHit))
+                const std::uint32_t rank = static_cast<std::uint32_t>(__popc(~busyMask & ((1u << laneId()) - 1u)));
+                std::uint32_t       id = base + rank; // IO may translate the work-item index into its own ray id
+                if (rank < granted && io.fetch(id, o, d, tmax, laneAnyHit))
                 {
                     rayIdx = id;
-                    // rayAabbIntersector, wgsl:438-445 / ray_intersection.cpp:92-99
-                    ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
-                    negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
-                    // +-inf inverse components (axis-parallel rays) stay on the fast path; NaN or zero ones (NaN or
-                    // infinite direction components) and non-finite origins do not.
-                    const bool exact = !sceneOrdered || !(ix == ix && iy == iy && iz == iz && ix != 0.0f && iy != 0.0f && iz != 0.0f &&
-                                                          isFiniteBits(o.x) && isFiniteBits(o.y) && isFiniteBits(o.z));
-                    cur = 0, rayNodes = 0, rayTris = 0;
-                    stackTop = stackBase;
-                    hit.tri = RF_NO_HIT;
-                    state = NODE;
-                    if (exact)
-                    {
-                        // Rays whose slab products can be NaN (zero / non-finite direction component, non-finite
-                        // origin, or a scene with unordered boxes) are traced to completion right here with the
-                        // literal test, so the hot loop above never sees them.
-                        traceExactRay();
-                        state = DONE;
-                    }
+                    startRay();
                 }
             }
         }
+        if (exhausted && busyMask == 0u && !gotWork) break;
     }
 #undef RF_ANY_HIT
 }
