@@ -249,6 +249,12 @@ rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled);
  * runs once `tri_min` lanes of a warp have a triangle pending, idle lanes are refilled once `refill_min`
  * are idle, `blocks_per_sm` persistent 256-thread blocks are launched per SM.  0 keeps a value. */
 rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refill_min, uint32_t blocks_per_sm);
+/* How a frame is scheduled (results never depend on it).  sub_frames (1..4, 0 keeps): the frame is traced as
+ * that many independent tile sets on separate CUDA streams so one set's traversal tail overlaps the other's
+ * work.  persistent_kernel (0/1, -1 keeps): experimental single-launch pipeline (csrc/mega.cuh) instead of one
+ * launch per stage.  variant (0..15, -1 keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling
+ * variant and block size of the traversal kernel. */
+rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t persistent_kernel, int32_t variant, int32_t block_threads);
 
 /* ---- the CPU traversal twin: nlrs::rayIntersectBvh (common/ray_intersection.hpp:43-49) --------- */
 

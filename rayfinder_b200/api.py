@@ -361,6 +361,9 @@ class ReferencePathTracer:
     def set_tuning(self, tri_min: int = 0, refill_min: int = 0, blocks_per_sm: int = 0) -> None:
         check(lib().rf_renderer_set_tuning(self._handle, tri_min, refill_min, blocks_per_sm))
 
+    def set_pipeline(self, sub_frames: int = 0, persistent_kernel: int = -1, variant: int = -1, block_threads: int = 0) -> None:
+        check(lib().rf_renderer_set_pipeline(self._handle, sub_frames, persistent_kernel, variant, block_threads))
+
 
 class TraversalScene:
     """Device-resident (bvhNodes, triangles) for the GPU twin of ``rayIntersectBvh``."""

@@ -104,6 +104,7 @@ SIGNATURES = {
     "rf_renderer_reset_stats": (C.c_int32, [_P]),
     "rf_renderer_set_stage_timing": (C.c_int32, [_P, C.c_int32]),
     "rf_renderer_set_tuning": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rf_renderer_set_pipeline": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "rf_traversal_scene_create": (C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(_P)]),
     "rf_traversal_scene_destroy": (None, [_P]),
     "rf_ray_intersect_bvh": (C.c_int32, [_P, _P, C.c_uint64, C.c_float, _P, _P, _P]),

@@ -4,10 +4,11 @@
 //
 // Compiled by nvcc for sm_100a only, with -fmad=false (see rf_vec.h).  There is no CPU fallback:
 // every entry point fails with RF_ERROR_CUDA when no device is usable.
-#include "kernels.cuh"
+#include "mega.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -198,6 +199,21 @@ void launchTrace(int variant, int block, Args&&... args)
     }
 }
 
+template<typename... Args>
+void launchMega(int variant, int block, int grid, cudaStream_t s, Args&&... args)
+{
+    if (block == 64)
+        k_mega<TRACE_DEFAULT_VARIANT, 64><<<grid, 64, 0, s>>>(args...);
+    else if (block == 128)
+        k_mega<TRACE_DEFAULT_VARIANT, 128><<<grid, 128, 0, s>>>(args...);
+    else if ((variant & 15) == 2)
+        k_mega<2, 256><<<grid, 256, 0, s>>>(args...);
+    else if ((variant & 15) == 1)
+        k_mega<1, 256><<<grid, 256, 0, s>>>(args...);
+    else
+        k_mega<TRACE_DEFAULT_VARIANT, 256><<<grid, 256, 0, s>>>(args...);
+}
+
 // =================================================================================================
 struct rf_renderer
 {
@@ -235,6 +251,9 @@ struct rf_renderer
         DeviceBuffer<HitRecord>     hits;
         DeviceBuffer<std::uint32_t> ownedTiles;
         DeviceBuffer<std::uint32_t> counters; // see counterSlots()
+        DeviceBuffer<std::uint32_t> meta, ready; // persistent-kernel mode: path meta, ready ring (mega.cuh)
+        DeviceBuffer<MegaControl>   control;
+        std::uint32_t               log2Cap = 0;
         PathQueue                   queues[2]{};
         std::uint64_t               capacity = 0; // paths
         std::uint32_t               numOwnedTiles = 0;
@@ -242,6 +261,7 @@ struct rf_renderer
     static constexpr int MAX_SUBFRAMES = 4;
     SubFrame    sub[MAX_SUBFRAMES];
     int         numSubFrames = 2;
+    bool        megakernel = false; // experimental: the frame as one persistent kernel (mega.cuh); slower so far
     cudaEvent_t forkEvent = nullptr;
 
     rf_render_parameters params{};
@@ -376,6 +396,12 @@ struct rf_renderer
                 RF_CUDA(sf.hits.allocate(need));
                 RF_CUDA(sf.ownedTiles.allocate(sf.numOwnedTiles));
                 if (!sf.counters.ptr) RF_CUDA(sf.counters.allocate(counterSlots(1024)));
+                if (!sf.control.ptr) RF_CUDA(sf.control.allocate(1));
+                sf.log2Cap = 0;
+                while ((1ull << sf.log2Cap) < need) ++sf.log2Cap;
+                if (sf.log2Cap > RING_ID_BITS) return setError(RF_ERROR_INVALID_ARGUMENT, "Framebuffer too large for one sub-frame.");
+                RF_CUDA(sf.meta.allocate(need));
+                RF_CUDA(sf.ready.allocate(1ull << sf.log2Cap));
                 for (int q = 0; q < 2; ++q)
                 {
                     float4* base = sf.queueMem.ptr + static_cast<std::uint64_t>(q) * 4 * need;
@@ -493,6 +519,7 @@ extern "C" rf_status rf_renderer_create(
         if (i > 0) RF_CUDA(cudaStreamCreateWithFlags(&r->sub[i].stream, cudaStreamNonBlocking));
         RF_CUDA(cudaEventCreateWithFlags(&r->sub[i].done, cudaEventDisableTiming));
     }
+    if (const char* e = std::getenv("RF_MEGAKERNEL")) r->megakernel = std::atoi(e) != 0;
     if (const char* e = std::getenv("RF_SUBFRAMES")) r->numSubFrames = std::min(std::max(std::atoi(e), 1), static_cast<int>(rf_renderer::MAX_SUBFRAMES));
 
     st = r->applyParams(desc->render_params);
@@ -567,7 +594,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     t.stagesUsed = 0;
     t.bounces = fp.numBounces;
     // Per-stage events are only meaningful when the stages do not overlap: one sub-frame on one stream.
-    const bool staged = r->stageTiming && r->numSubFrames == 1;
+    const bool staged = r->stageTiming && r->numSubFrames == 1; // (also selects the staged pipeline: one launch per stage)
     const auto stageMark = [&]() -> cudaError_t {
         if (!staged) return cudaSuccess;
         if (t.stagesUsed >= t.stages.size())
@@ -603,6 +630,32 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         std::uint32_t* ctr = sf.counters.ptr;
         RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(fp.numBounces) * sizeof(std::uint32_t), ss));
         std::uint32_t* const cursors = ctr + fp.numBounces + 1u;
+        if (r->megakernel && !staged)
+        {
+            RF_CUDA(cudaMemsetAsync(sf.ready.ptr, 0, (1ull << sf.log2Cap) * sizeof(std::uint32_t), ss));
+            k_raygen_mega<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], sf.meta.ptr, sf.ready.ptr, sf.log2Cap, &ctr[0],
+                                                              r->radiance.ptr, r->stats.ptr);
+            k_mega_init<<<1, 1, 0, ss>>>(sf.control.ptr, &ctr[0]);
+            launchMega(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], sf.meta.ptr, r->radiance.ptr, sf.control.ptr, sf.ready.ptr,
+                       sf.log2Cap, r->stats.ptr);
+            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+            if (std::getenv("RF_DEBUG_MEGA"))
+            {
+                MegaControl   c{};
+                std::uint32_t n = 0;
+                cudaStreamSynchronize(ss);
+                cudaMemcpy(&c, sf.control.ptr, sizeof(c), cudaMemcpyDeviceToHost);
+                cudaMemcpy(&n, &ctr[0], sizeof(n), cudaMemcpyDeviceToHost);
+                std::fprintf(stderr, "[mega] sub-frame %d: paths %u head %u tail %u avail %d live 0x%x log2Cap %u (%s)\n", i, n, c.head, c.tail, c.avail,
+                             c.live, sf.log2Cap, cudaGetErrorString(cudaGetLastError()));
+            }
+            if (i > 0)
+            {
+                RF_CUDA(cudaEventRecord(sf.done, ss));
+                RF_CUDA(cudaStreamWaitEvent(s, sf.done, 0));
+            }
+            continue;
+        }
 
         k_raygen<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
@@ -755,19 +808,22 @@ extern "C" rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enable
 extern "C" rf_status rf_renderer_set_tuning(rf_renderer* r, std::uint32_t triMin, std::uint32_t refillMin, std::uint32_t blocksPerSm)
 {
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: null renderer");
-    if (triMin > 32u || refillMin > 32u || (blocksPerSm & 0xFFu) > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
-    if (blocksPerSm & 0x100u) r->variant = static_cast<int>((blocksPerSm >> 12) & 15u); // experimental: bits 12-15 = kernel variant
-    if (blocksPerSm & 0x10000u) r->traceBlock = 64 << ((blocksPerSm >> 17) & 3u);               // experimental: bits 17-18 = log2(block / 64)
-    if (r->traceBlock > 256) r->traceBlock = 256;
-    if (blocksPerSm & 0x200u)                                                                  // experimental: bits 10-11 = sub-frames - 1
-    {
-        const int n = static_cast<int>((blocksPerSm >> 10) & 3u) + 1;
-        if (n != r->numSubFrames) r->numSubFrames = n, r->tilesDirty = true;
-    }
-    blocksPerSm &= 0xFFu;
+    if (triMin > 32u || refillMin > 32u || blocksPerSm > 8u) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tuning: value out of range");
     if (triMin) r->tuning.triMin = triMin;
     if (refillMin) r->tuning.refillMin = refillMin;
     if (blocksPerSm) r->traceBlocksPerSm = static_cast<int>(blocksPerSm);
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_set_pipeline(rf_renderer* r, std::int32_t subFrames, std::int32_t persistentKernel, std::int32_t variant, std::int32_t blockThreads)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_pipeline: null renderer");
+    if (subFrames > rf_renderer::MAX_SUBFRAMES || variant > 15 || (blockThreads != 0 && blockThreads != 64 && blockThreads != 128 && blockThreads != 256))
+        return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_pipeline: value out of range");
+    if (subFrames > 0 && subFrames != r->numSubFrames) r->numSubFrames = subFrames, r->tilesDirty = true;
+    if (persistentKernel >= 0) r->megakernel = persistentKernel != 0;
+    if (variant >= 0) r->variant = variant;
+    if (blockThreads > 0) r->traceBlock = blockThreads;
     return RF_OK;
 }
 

@@ -128,6 +128,34 @@ __device__ __forceinline__ bool slotToPixel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// The primary ray of fragment (px, py): vsMain/fsMain:10-17,34-54, animatedBlueNoise:603-616 (tabulated per
+// sample index), generateCameraRay:237-245 with the thin lens (pointInUnitDisk:596-600).
+__device__ __forceinline__ void primaryRay(
+    const FrameParams& fp, const SceneDevice& scene, const std::uint32_t px, const std::uint32_t py, std::uint32_t& idx, V3& origin, V3& dir)
+{
+    // fragment centre -> texCoord -> coord
+    const float u = __fdiv_rn(static_cast<float>(px) + 0.5f, static_cast<float>(fp.width));
+    const float v = __fdiv_rn(static_cast<float>(py) + 0.5f, static_cast<float>(fp.height));
+    const std::uint32_t cx = static_cast<std::uint32_t>(u * static_cast<float>(fp.width));
+    const std::uint32_t cy = static_cast<std::uint32_t>(v * static_cast<float>(fp.height));
+    idx = cy * fp.width + cx;
+
+    const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+    const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+    const float         ux = lut.ux[bn.x], uy = lut.uy[bn.y];
+
+    // jitter = blueNoise / vec2f(dimensions); generateCameraRay(bn, camera, u + j.x, (1 - v) + j.y)
+    const float su = u + __fdiv_rn(ux, static_cast<float>(fp.width));
+    const float sv = (1.0f - v) + __fdiv_rn(uy, static_cast<float>(fp.height));
+
+    const float r = __fsqrt_rn(ux);
+    const float lensX = fp.camera.lens_radius * (r * lut.cosPhi[bn.y]);
+    const float lensY = fp.camera.lens_radius * (r * lut.sinPhi[bn.y]);
+    const V3    lensOffset = lensX * v3(fp.camera.right) + lensY * v3(fp.camera.up);
+    origin = v3(fp.camera.origin) + lensOffset;
+    dir = normalize(((v3(fp.camera.lower_left_corner) + su * v3(fp.camera.horizontal)) + sv * v3(fp.camera.vertical)) - origin);
+}
+
 __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
     const FrameParams fp,
     const SceneDevice scene,
@@ -147,32 +175,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(
         const std::uint32_t dst = warpAppend(outCount, valid);
         if (!valid) continue;
         ++generated;
-
-        // vsMain/fsMain:10-17,34-43: fragment centre -> texCoord -> coord.
-        const float u = __fdiv_rn(static_cast<float>(px) + 0.5f, static_cast<float>(fp.width));
-        const float v = __fdiv_rn(static_cast<float>(py) + 0.5f, static_cast<float>(fp.height));
-        const std::uint32_t cx = static_cast<std::uint32_t>(u * static_cast<float>(fp.width));
-        const std::uint32_t cy = static_cast<std::uint32_t>(v * static_cast<float>(fp.height));
-        const std::uint32_t idx = cy * fp.width + cx;
-
-        // animatedBlueNoise (tabulated per sample index).
-        const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
-        const SampleLutRow& lut = scene.lut[fp.sampleIndex];
-        const float         ux = lut.ux[bn.x], uy = lut.uy[bn.y];
-
-        // jitter = blueNoise / vec2f(dimensions); generateCameraRay(bn, camera, u + j.x, (1 - v) + j.y)
-        const float su = u + __fdiv_rn(ux, static_cast<float>(fp.width));
-        const float sv = (1.0f - v) + __fdiv_rn(uy, static_cast<float>(fp.height));
-
-        // pointInUnitDisk (wgsl:596-600) and the thin lens (wgsl:238-241).
-        const float r = __fsqrt_rn(ux);
-        const float lensX = fp.camera.lens_radius * (r * lut.cosPhi[bn.y]);
-        const float lensY = fp.camera.lens_radius * (r * lut.sinPhi[bn.y]);
-        const V3    lensOffset = lensX * v3(fp.camera.right) + lensY * v3(fp.camera.up);
-        const V3    origin = v3(fp.camera.origin) + lensOffset;
-        const V3    dir = normalize(
-            ((v3(fp.camera.lower_left_corner) + su * v3(fp.camera.horizontal)) + sv * v3(fp.camera.vertical)) - origin);
-
+        std::uint32_t idx;
+        V3            origin, dir;
+        primaryRay(fp, scene, px, py, idx, origin, dir);
         out.originPix[dst] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(idx));
         out.direction[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
         out.throughput[dst] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
@@ -198,6 +203,89 @@ __device__ __forceinline__ float skyRadianceChannel(const rf_sky_state& sky, con
     const float  radianceLhs = 1.0f + p[0] * expf(__fdiv_rn(p[1], cosTheta + 0.01f));
     const float  radianceRhs = p[2] + p[3] * expM + p[5] * rayM + p[6] * mieM + p[7] * zenith;
     return r * (radianceLhs * radianceRhs);
+}
+
+// rayColor miss branch, wgsl:212-229: sky radiance along the (possibly unnormalised) direction v.
+__device__ __forceinline__ V3 skyForMiss(const FrameParams& fp, const V3 v, const V3 sunDir)
+{
+    const float theta = acosf(v.y);
+    float       cosSun = dot(v, sunDir);
+    cosSun = fminf(fmaxf(cosSun, -1.0f), 1.0f);
+    const float gamma = acosf(cosSun);
+    return v3(skyRadianceChannel(fp.sky, theta, gamma, 0), skyRadianceChannel(fp.sky, theta, gamma, 1), skyRadianceChannel(fp.sky, theta, gamma, 2));
+}
+
+// rayColor hit branch, wgsl:191-211, for the final (closest) accepted triangle of a path at pixel `idx`:
+// hit point + attributes (wgsl:393-400), albedo (:553-565), sun sample (:288-292), NEE term without
+// visibility (:196-203), Lambert scatter (:295-301).
+struct SurfaceShade
+{
+    V3 p, wi, nextThroughput, contribution;
+};
+__device__ __forceinline__ SurfaceShade shadeSurfaceHit(
+    const FrameParams& fp, const SceneDevice& scene, const HitRecord& hit, const std::uint32_t idx, const V3 throughput, const V3 sunDir)
+{
+    SurfaceShade out;
+    // Intersection of the final (closest) accepted triangle, wgsl:393-400.
+    out.p = hitPoint(scene.tris, hit);
+    const float  b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
+    const float4 a0 = ldg4(scene.vattr + 5 * hit.tri + 0);
+    const float4 a1 = ldg4(scene.vattr + 5 * hit.tri + 1);
+    const float4 a2 = ldg4(scene.vattr + 5 * hit.tri + 2);
+    const float4 a3 = ldg4(scene.vattr + 5 * hit.tri + 3);
+    const float4 a4 = ldg4(scene.vattr + 5 * hit.tri + 4);
+    const V3     nrm = (b0 * v3(a0.x, a0.y, a0.z) + b1 * v3(a1.x, a1.y, a1.z)) + b2 * v3(a2.x, a2.y, a2.z);
+    const float  tu = (b0 * a3.x + b1 * a3.z) + b2 * a4.x;
+    const float  tv = (b0 * a3.y + b1 * a3.w) + b2 * a4.y;
+    std::uint32_t texIdx = __float_as_uint(a4.z);
+    texIdx = min(texIdx, fp.numTextures - 1u); // robust buffer access
+
+    // textureLookup, wgsl:553-565.
+    const uint4         desc = scene.texDesc[texIdx];
+    const float         fu = wgslFract(tu), fv = wgslFract(tv);
+    const std::uint32_t tj = static_cast<std::uint32_t>(fu * static_cast<float>(desc.x));
+    const std::uint32_t ti = static_cast<std::uint32_t>(fv * static_cast<float>(desc.y));
+    std::uint64_t       texel = static_cast<std::uint64_t>(desc.z) + static_cast<std::uint64_t>(ti * desc.x + tj);
+    texel = texel < fp.numTexels ? texel : fp.numTexels - 1u; // robust buffer access clamps
+    const std::uint32_t bgra = __ldg(scene.texels + texel);
+    const V3            albedo = v3(scene.srgbLut[(bgra >> 16) & 0xFFu], scene.srgbLut[(bgra >> 8) & 0xFFu], scene.srgbLut[bgra & 0xFFu]);
+
+    // Per-pixel sample (the same vec2 for every decision of the path, wgsl:194,209).
+    const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
+    const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+    const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+    const float         ux = lut.ux[bn.x];
+    const float         cosPhi = lut.cosPhi[bn.y], sinPhi = lut.sinPhi[bn.y];
+
+    // sampleSolarDiskDirection -> directionInCone, wgsl:288-292,569-579.
+    const float cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
+    const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+    const V3    lightDir = onbTransform(sunDir, v3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+
+    // rayColor hit branch, wgsl:191-203.
+    const float FRAC_1_PI = 0.31830987f;
+    const V3    lightIntensity = v3(fp.sky.solar_radiances[0], fp.sky.solar_radiances[1], fp.sky.solar_radiances[2]);
+    const V3    brdf = albedo * FRAC_1_PI;
+    const V3    reflectance = brdf * dot(nrm, lightDir);
+    out.contribution = (throughput * lightIntensity) * reflectance;
+
+    // evalImplicitLambertian -> directionInCosineWeightedHemisphere, wgsl:295-301,583-592.
+    const float hemiSin = __fsqrt_rn(1.0f - ux);
+    out.wi = onbTransform(nrm, v3(cosPhi * hemiSin, sinPhi * hemiSin, __fsqrt_rn(ux)));
+    out.nextThroughput = throughput * albedo;
+    return out;
+}
+
+// The sun sample of pixel `idx` (sampleSolarDiskDirection, wgsl:288-292): direction of its shadow rays.
+__device__ __forceinline__ V3 sunSampleDirection(const FrameParams& fp, const SceneDevice& scene, const std::uint32_t idx, const V3 sunDir)
+{
+    const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
+    const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
+    const SampleLutRow& lut = scene.lut[fp.sampleIndex];
+    const float         ux = lut.ux[bn.x];
+    const float         cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
+    const float         sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+    return onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,17 +325,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
 
         if (live && !isHit)
         {
-            // rayColor miss branch, wgsl:212-229.
-            const V3    v = v3(dir.x, dir.y, dir.z);
-            const float theta = acosf(v.y);
-            float       cosSun = dot(v, sunDir);
-            cosSun = fminf(fmaxf(cosSun, -1.0f), 1.0f);
-            const float gamma = acosf(cosSun);
-            const V3    sky = v3(
-                skyRadianceChannel(fp.sky, theta, gamma, 0),
-                skyRadianceChannel(fp.sky, theta, gamma, 1),
-                skyRadianceChannel(fp.sky, theta, gamma, 2));
-            float4 rad = radiance[idx];
+            const V3 sky = skyForMiss(fp, v3(dir.x, dir.y, dir.z), sunDir);
+            float4   rad = radiance[idx];
             rad.x += thr.x * sky.x, rad.y += thr.y * sky.y, rad.z += thr.z * sky.z;
             radiance[idx] = rad;
         }
@@ -255,54 +334,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
         const std::uint32_t dst = warpAppend(outCount, isHit);
         if (!isHit) continue;
 
-        // Intersection of the final (closest) accepted triangle, wgsl:393-400.
-        const V3     p = hitPoint(scene.tris, hit);
-        const float  b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
-        const float4 a0 = ldg4(scene.vattr + 5 * hit.tri + 0);
-        const float4 a1 = ldg4(scene.vattr + 5 * hit.tri + 1);
-        const float4 a2 = ldg4(scene.vattr + 5 * hit.tri + 2);
-        const float4 a3 = ldg4(scene.vattr + 5 * hit.tri + 3);
-        const float4 a4 = ldg4(scene.vattr + 5 * hit.tri + 4);
-        const V3     nrm = (b0 * v3(a0.x, a0.y, a0.z) + b1 * v3(a1.x, a1.y, a1.z)) + b2 * v3(a2.x, a2.y, a2.z);
-        const float  tu = (b0 * a3.x + b1 * a3.z) + b2 * a4.x;
-        const float  tv = (b0 * a3.y + b1 * a3.w) + b2 * a4.y;
-        std::uint32_t texIdx = __float_as_uint(a4.z);
-        texIdx = min(texIdx, fp.numTextures - 1u); // robust buffer access
-
-        // textureLookup, wgsl:553-565.
-        const uint4         desc = scene.texDesc[texIdx];
-        const float         fu = wgslFract(tu), fv = wgslFract(tv);
-        const std::uint32_t tj = static_cast<std::uint32_t>(fu * static_cast<float>(desc.x));
-        const std::uint32_t ti = static_cast<std::uint32_t>(fv * static_cast<float>(desc.y));
-        std::uint64_t       texel = static_cast<std::uint64_t>(desc.z) + static_cast<std::uint64_t>(ti * desc.x + tj);
-        texel = texel < fp.numTexels ? texel : fp.numTexels - 1u; // robust buffer access clamps
-        const std::uint32_t bgra = __ldg(scene.texels + texel);
-        const V3            albedo = v3(scene.srgbLut[(bgra >> 16) & 0xFFu], scene.srgbLut[(bgra >> 8) & 0xFFu], scene.srgbLut[bgra & 0xFFu]);
-
-        // Per-pixel sample (the same vec2 for every decision of the path, wgsl:194,209).
-        const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
-        const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
-        const SampleLutRow& lut = scene.lut[fp.sampleIndex];
-        const float         ux = lut.ux[bn.x];
-        const float         cosPhi = lut.cosPhi[bn.y], sinPhi = lut.sinPhi[bn.y];
-
-        // sampleSolarDiskDirection -> directionInCone, wgsl:288-292,569-579.
-        const float cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
-        const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
-        const V3    lightDir = onbTransform(sunDir, v3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
-
-        // rayColor hit branch, wgsl:191-203.
-        const float FRAC_1_PI = 0.31830987f;
-        const V3    lightIntensity = v3(fp.sky.solar_radiances[0], fp.sky.solar_radiances[1], fp.sky.solar_radiances[2]);
-        const V3    brdf = albedo * FRAC_1_PI;
-        const V3    reflectance = brdf * dot(nrm, lightDir);
-        const V3    throughput = v3(thr.x, thr.y, thr.z);
-        const V3    contribution = (throughput * lightIntensity) * reflectance;
-
-        // evalImplicitLambertian -> directionInCosineWeightedHemisphere, wgsl:295-301,583-592.
-        const float hemiSin = __fsqrt_rn(1.0f - ux);
-        const V3    wi = onbTransform(nrm, v3(cosPhi * hemiSin, sinPhi * hemiSin, __fsqrt_rn(ux)));
-        const V3    nextThroughput = throughput * albedo;
+        const SurfaceShade sh = shadeSurfaceHit(fp, scene, hit, idx, v3(thr.x, thr.y, thr.z), sunDir);
+        const V3           p = sh.p, wi = sh.wi, nextThroughput = sh.nextThroughput, contribution = sh.contribution;
 
         out.originPix[dst] = make_float4(p.x, p.y, p.z, oPix.w);
         out.direction[dst] = make_float4(wi.x, wi.y, wi.z, 0.0f);
@@ -342,17 +375,9 @@ struct TraceIO : CursorSource
             o = v3(oo.x, oo.y, oo.z), d = v3(dd.x, dd.y, dd.z);
             return true;
         }
-        const float4        oPix = shadowQueue.originPix[id];
-        const std::uint32_t idx = __float_as_uint(oPix.w);
-        const std::uint32_t cx = idx % fp.width, cy = idx / fp.width;
-        const uchar2        bn = scene.blueNoise[(cy % BLUE_NOISE_HEIGHT) * BLUE_NOISE_WIDTH + (cx % BLUE_NOISE_WIDTH)];
-        const SampleLutRow& lut = scene.lut[fp.sampleIndex];
-        const float         ux = lut.ux[bn.x];
-        // sampleSolarDiskDirection -> directionInCone, wgsl:288-292,569-579
-        const float cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
-        const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+        const float4 oPix = shadowQueue.originPix[id];
         o = v3(oPix.x, oPix.y, oPix.z);
-        d = onbTransform(sunDir, v3(lut.cosPhi[bn.y] * sinTheta, lut.sinPhi[bn.y] * sinTheta, cosTheta));
+        d = sunSampleDirection(fp, scene, __float_as_uint(oPix.w), sunDir);
         return true;
     }
     __device__ __forceinline__ bool finish(

@@ -302,3 +302,26 @@ def test_texture_limit_error_message(duck_pt):
     with pytest.raises(rf.RayfinderError) as e:
         rf.ReferencePathTracer(rf.RenderParameters((8, 8), cam, rf.SamplingParams(1, 1)), (8, 8), scene)
     assert str(e.value) == f"Texture buffer size ({huge.size * 4}) exceeds maxStorageBufferBindingSize ({1 << 30})."
+
+
+@pytest.mark.parametrize("sub_frames,persistent,variant,block,tri_min,refill_min", [
+    (1, 0, 3, 256, 4, 4), (2, 0, 3, 256, 4, 4), (4, 0, 2, 64, 1, 1), (3, 0, 1, 128, 32, 32), (1, 0, 11, 256, 8, 16),
+    (1, 1, 3, 256, 4, 4), (2, 1, 3, 128, 2, 8)])
+def test_results_do_not_depend_on_scheduling(duck_pt, sub_frames, persistent, variant, block, tri_min, refill_min):
+    """Sub-frame pipelining, the experimental persistent kernel, the compile-time scheduling variants, block sizes and
+    the run-time knobs change how warps are kept busy — never a counter or a pixel."""
+    w, h, spp, bounces = 150, 70, 2, 5
+    cam = rf.bvh_visualizer_camera(duck_pt.bvh_nodes, w, h)
+    ren, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
+    ren.set_pipeline(1, 0, 3, 256)
+    ren.render(), ren.render()
+    ref_img, _ = ren.read_hdr()
+    ref_stats = ren.stats()
+    ren2, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
+    ren2.set_tuning(tri_min, refill_min, 4)
+    ren2.set_pipeline(sub_frames, persistent, variant, block)
+    ren2.render(), ren2.render()
+    img, _ = ren2.read_hdr()
+    for key in O.COUNTER_NAMES:
+        assert ren2.stats()[key] == ref_stats[key], key
+    assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))

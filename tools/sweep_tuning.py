@@ -25,11 +25,12 @@ def main():
     pt = rfa.load_scene("Sponza")
     params = rf.RenderParameters((w, h), rf.fly_camera(w, h), rf.SamplingParams(1, bounces), rf.Sky(), 0.25)
     ren = rf.ReferencePathTracer(params, (w, h), rf.SceneArrays.from_pt(pt))
-    ren.set_stage_timing(True)
+    ren.set_stage_timing(os.environ.get('RF_STAGE_TIMING', '0') == '1')
     tri_list, refill_list = ints(1, "2,4,8"), ints(2, "4")
-    blocks_list, variant_list, sort_list, bs_list = ints(3, "4"), ints(4, "3"), ints(5, "1"), ints(6, "256")
-    for bs, sort, variant, blocks, tri, refill in itertools.product(bs_list, sort_list, variant_list, blocks_list, tri_list, refill_list):
-        ren.set_tuning(tri, refill, blocks | 0x100 | (variant << 12) | 0x200 | (sort << 10) | 0x10000 | ({64: 0, 128: 1, 256: 2}[bs] << 17))
+    blocks_list, variant_list, sort_list, bs_list, mega_list = ints(3, "4"), ints(4, "3"), ints(5, "1"), ints(6, "256"), ints(7, "1")
+    for mega, bs, sort, variant, blocks, tri, refill in itertools.product(mega_list, bs_list, sort_list, variant_list, blocks_list, tri_list, refill_list):
+        ren.set_tuning(tri, refill, blocks)
+        ren.set_pipeline(sort + 1, mega, variant, bs)
         for k in range(frames + 1):
             if k == 1:
                 ren.reset_stats()
@@ -38,7 +39,7 @@ def main():
             ren.render()
         s = ren.stats()
         rays = s["closest_rays"] + s["shadow_rays"]
-        print(f"block={bs} subframes={sort + 1} variant={variant:2d} (steps={(variant & 3) + 1} leaf={(variant >> 2) & 1} branchy={(variant >> 3) & 1}) "
+        print(f"mega={mega} block={bs} subframes={sort + 1} variant={variant:2d} (steps={(variant & 3) + 1} leaf={(variant >> 2) & 1} branchy={(variant >> 3) & 1}) "
               f"blocks={blocks} tri_min={tri:2d} refill_min={refill:2d}  total={s['device_ms_total'] / frames:7.3f} ms  "
               f"trace={s['device_ms_trace'] / frames:7.3f} "
               f"shade={s['device_ms_shade'] / frames:6.3f}  Mrays/s={rays / s['device_ms_total'] / 1e3:8.1f}", flush=True)
