@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "librayfinder_b200.so"
+# RAYFINDER_B200_LIB selects another build of the same library (kernel experiments); there is still no fallback.
+LIB_PATH = Path(os.environ.get("RAYFINDER_B200_LIB", _PKG / "librayfinder_b200.so"))
 
 RF_OK = 0
 RF_ERROR_INVALID_ARGUMENT = 1

@@ -406,8 +406,11 @@ struct TraceIO : CursorSource
     }
 };
 
+#ifndef RF_TRACE_MIN_BLOCKS
+#define RF_TRACE_MIN_BLOCKS 4
+#endif
 template<int VARIANT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_trace(
+__global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_trace(
     const FrameParams    fp,
     const SceneDevice    scene,
     const PathQueue      closestQueue,

@@ -13,8 +13,9 @@
 //   ready ring     = device ring buffer of path ids; producers reserve with atomicAdd(tail), consumers with a
 //                    counting semaphore (`avail`) + atomicAdd(head); entries carry a lap tag so a consumer can
 //                    tell a published entry from a stale one without anyone resetting slots
-//   shade batch    = every warp collects the paths whose closest-hit ray it finished in a 64-entry shared-memory
-//                    buffer and shades 32 of them at a time (dense: one path per lane), appending survivors
+//   shade batch    = warp specialisation: in every block all warps but one only trace; they hand the paths whose
+//                    closest-hit ray they finished to the block's shading warp through a shared-memory ring, and
+//                    that warp shades 32 of them at a time (dense: one path per lane), appending the survivors
 //                    to the ready ring — this is the stream compaction of live paths
 //   termination    = `live` counts paths that have not ended; a warp that runs dry reports the paths it ended and
 //                    leaves when live == 0
@@ -92,105 +93,34 @@ __global__ void k_mega_init(MegaControl* ctl, const std::uint32_t* pathCount)
     ctl->live = n;
 }
 
-// Shading of entries [first, first + n) of one warp's buffer, one path per lane; survivors go back to the
-// ready ring (stream compaction).  Out of line: called once per 32 finished closest-hit rays, and its ~60
-// registers must not weigh on the traversal loop.  Returns nothing; ended paths are added to *deadCount.
-__device__ __noinline__ void megaShadeBatch(
-    const FrameParams*  fpPtr,
-    const SceneDevice*  scenePtr,
-    const PathQueue     paths,
-    std::uint32_t*      meta,
-    float4*             radiance,
-    MegaControl*        ctl,
-    std::uint32_t*      ready,
-    const std::uint32_t log2Cap,
-    const uint4*        shadeBuf,
-    std::uint32_t*      shadeCount,
-    std::uint32_t*      deadCount,
-    const std::uint32_t first,
-    const std::uint32_t n)
-{
-    const FrameParams& fp = *fpPtr;
-    const SceneDevice& scene = *scenePtr;
-    const V3           sunDir = v3(fp.sky.sun_direction);
-    __syncwarp();
-    const bool    mine = laneId() < n;
-    bool          survives = false, ended = false;
-    std::uint32_t id = 0;
-    if (mine)
-    {
-        const uint4 e = shadeBuf[first + laneId()];
-        id = e.x;
-        const HitRecord     hit{e.y, __uint_as_float(e.z), __uint_as_float(e.w), 0.0f};
-        const std::uint32_t m = __ldcg(meta + id);
-        const std::uint32_t bounce = m & META_BOUNCE_MASK;
-        const float4        oPix = ldcg4(paths.originPix + id);
-        const float4        thr = ldcg4(paths.throughput + id);
-        const std::uint32_t idx = __float_as_uint(oPix.w);
-        if (hit.tri == RF_NO_HIT)
-        {
-            const float4 dir = ldcg4(paths.direction + id);
-            const V3     sky = skyForMiss(fp, v3(dir.x, dir.y, dir.z), sunDir);
-            float4       rad = ldcg4(radiance + idx);
-            rad.x += thr.x * sky.x, rad.y += thr.y * sky.y, rad.z += thr.z * sky.z;
-            __stcg(radiance + idx, rad);
-            ended = true;
-        }
-        else
-        {
-            const SurfaceShade sh = shadeSurfaceHit(fp, scene, hit, idx, v3(thr.x, thr.y, thr.z), sunDir);
-            __stcg(paths.originPix + id, make_float4(sh.p.x, sh.p.y, sh.p.z, oPix.w));
-            __stcg(paths.direction + id, make_float4(sh.wi.x, sh.wi.y, sh.wi.z, 0.0f));
-            __stcg(paths.throughput + id, make_float4(sh.nextThroughput.x, sh.nextThroughput.y, sh.nextThroughput.z, 0.0f));
-            __stcg(paths.contribution + id, make_float4(sh.contribution.x, sh.contribution.y, sh.contribution.z, 0.0f));
-            // every hit casts a shadow ray; the path goes on unless this was the last bounce (rayColor:205-207)
-            __stcg(meta + id, (bounce + 1u) | META_DO_SHADOW | (bounce < fp.numBounces ? META_DO_CLOSEST : 0u));
-            survives = true;
-        }
-    }
-    const unsigned endedMask = __ballot_sync(0xFFFFFFFFu, ended);
-    const unsigned mask = __ballot_sync(0xFFFFFFFFu, survives);
-    if (mask != 0u)
-    {
-        const std::uint32_t count = static_cast<std::uint32_t>(__popc(mask));
-        std::uint32_t       pos = 0;
-        if (laneId() == 0u) pos = atomicAdd(&ctl->tail, count);
-        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        __threadfence(); // path state before its ring entry
-        if (survives)
-        {
-            const std::uint32_t at = pos + static_cast<std::uint32_t>(__popc(mask & ((1u << laneId()) - 1u)));
-            *reinterpret_cast<volatile std::uint32_t*>(ready + (at & ((1u << log2Cap) - 1u))) = ringEntry(at, log2Cap, id);
-        }
-        __threadfence();
-        __syncwarp();
-        if (laneId() == 0u) atomicAdd(&ctl->avail, static_cast<int>(count));
-    }
-    if (laneId() == 0u)
-    {
-        *shadeCount = first;
-        *deadCount += static_cast<std::uint32_t>(__popc(endedMask));
-    }
-    __syncwarp();
-}
+// ---- warp-specialised persistent kernel -------------------------------------------------------------
+// A block = TRAVERSAL_WARPS warps that only trace (traceRays with MegaIO) + 1 warp that only shades.  Finished
+// closest-hit rays go from the traversal lanes to the shading warp through a shared-memory ring; the shading
+// warp handles 32 paths at a time (dense) and appends the survivors to the global ready ring.  Keeping the
+// shading code out of the traversal warps' instruction stream keeps both under 64 registers without spills.
+constexpr std::uint32_t HIT_RING_CAP = 128; // entries per block; a power of two (every KB of shared memory is a KB less L1)
 
-// IO of the persistent kernel for traceRays.  It holds no per-lane state (everything a lane needs between
-// fetch and finish is re-read from the path record), so nothing but the traversal state lives in registers
-// across the hot loop.
+template<int BLOCK>
+struct MegaShared
+{
+    static constexpr int WARPS = BLOCK / 32;
+    uint4              hitRing[HIT_RING_CAP];   // (path id, tri, u, v) of finished closest-hit rays
+    std::uint32_t      hitSeq[HIT_RING_CAP];    // lap tag of the entry (position / CAP + 1), written after the entry
+    std::uint32_t      ringTail;                // reserved positions (traversal lanes, atomicAdd)
+    std::uint32_t      ringHead;                // consumed positions (shading warp)
+    std::uint32_t      traversalAlive;          // traversal warps still running
+    std::uint32_t      deadCount[WARPS];        // paths ended by the warp and not yet reported to ctl->live
+    std::uint32_t      starved[WARPS];          // consecutive empty-handed waits (back-off)
+    unsigned long long starvedSince[WARPS];     // %globaltimer (ns) of the first of them (watchdog)
+    std::uint32_t      blockStats[6];           // closest {rays, nodes, tris}, shadow {rays, nodes, tris}
+};
+
+// IO of the traversal warps.  It holds no per-lane state (everything a lane needs between fetch and finish is
+// re-read from the path record), so nothing but the traversal state lives in registers across the hot loop.
 template<int BLOCK>
 struct MegaIO
 {
-    static constexpr int WARPS = BLOCK / 32;
-    struct Shared
-    {
-        uint4         shadeBuf[WARPS][64];   // (path id, tri, u, v) of finished closest-hit rays, per warp
-        std::uint32_t shadeCount[WARPS];
-        std::uint32_t deadCount[WARPS];      // paths ended by the warp and not yet reported to ctl->live
-        std::uint32_t starved[WARPS];        // consecutive empty-handed waits (back-off)
-        unsigned long long starvedSince[WARPS]; // %globaltimer (ns) of the first of them (watchdog)
-        std::uint32_t blockStats[6];         // closest {rays, nodes, tris}, shadow {rays, nodes, tris}
-    };
-
+    using Shared = MegaShared<BLOCK>;
     const FrameParams& fp;
     const SceneDevice& scene;
     const PathQueue    paths; // path state, indexed by path id
@@ -203,7 +133,6 @@ struct MegaIO
 
     __device__ __forceinline__ int warpId() const { return threadIdx.x >> 5; }
 
-    // ---- consumer side -------------------------------------------------------------------------------
     __device__ __forceinline__ std::uint32_t tryAcquire(const std::uint32_t want, std::uint32_t& base) const
     {
         std::uint32_t granted = 0, b = 0;
@@ -220,42 +149,18 @@ struct MegaIO
         return granted;
     }
 
-    __device__ __forceinline__ void shadeBatch(const std::uint32_t first, const std::uint32_t n) const
-    {
-        const int w = warpId();
-        megaShadeBatch(&fp, &scene, paths, meta, radiance, ctl, ready, log2Cap, sh.shadeBuf[w], &sh.shadeCount[w], &sh.deadCount[w], first, n);
-    }
-
     __device__ __forceinline__ std::uint32_t acquire(const std::uint32_t want, const bool mayWait, std::uint32_t& base, bool& exhausted) const
     {
-        const int w = warpId();
-        // shade what this warp has collected before asking for more rays
-        std::uint32_t pending = *reinterpret_cast<volatile std::uint32_t*>(&sh.shadeCount[w]);
-        while (pending >= 32u)
-        {
-            shadeBatch(pending - 32u, 32u);
-            pending -= 32u;
-        }
-        std::uint32_t granted = tryAcquire(want, base);
-        if (granted < want && pending != 0u)
-        {
-            // the ring ran dry: do not sit on a partial batch — its survivors are somebody's next rays
-            shadeBatch(0u, pending);
-            pending = 0u;
-            if (granted == 0u) granted = tryAcquire(want, base);
-        }
+        const int           w = warpId();
+        const std::uint32_t granted = tryAcquire(want, base);
         if (granted == 0u && mayWait)
         {
-            // nothing to trace and nothing to shade: report the paths this warp ended, then look at the frame
+            // nothing to trace: report the paths this warp ended, then look at the frame
             std::uint32_t live = 0;
             if (laneId() == 0u)
             {
-                const std::uint32_t ended = *reinterpret_cast<volatile std::uint32_t*>(&sh.deadCount[w]);
-                if (ended != 0u)
-                {
-                    atomicSub(&ctl->live, ended);
-                    sh.deadCount[w] = 0u;
-                }
+                const std::uint32_t ended = atomicExch(&sh.deadCount[w], 0u);
+                if (ended != 0u) atomicSub(&ctl->live, ended);
                 live = *reinterpret_cast<volatile std::uint32_t*>(&ctl->live);
                 if (live != 0u)
                 {
@@ -328,7 +233,6 @@ struct MegaIO
         atomicAdd(st + 0, 1u);
         atomicAdd(st + 1, visited);
         atomicAdd(st + 2, tested);
-        const int w = warpId();
         if (anyHit)
         {
             // shadowRay result folded into the NEE term, rayColor:203
@@ -351,15 +255,118 @@ struct MegaIO
                 anyHitNext = false;
                 return true;
             }
-            atomicAdd(&sh.deadCount[w], 1u); // last bounce: the path ends with its shadow ray
+            atomicAdd(&sh.deadCount[warpId()], 1u); // last bounce: the path ends with its shadow ray
             return false;
         }
-        // closest-hit ray done: queue the path for this warp's next shade batch
-        const std::uint32_t pos = atomicAdd(&sh.shadeCount[w], 1u);
-        sh.shadeBuf[w][pos] = make_uint4(id, hit.tri, __float_as_uint(hit.u), __float_as_uint(hit.v));
+        // closest-hit ray done: hand the path to the block's shading warp
+        const std::uint32_t pos = atomicAdd(&sh.ringTail, 1u);
+        while (pos - *reinterpret_cast<volatile std::uint32_t*>(&sh.ringHead) >= HIT_RING_CAP) {} // back-pressure (rare)
+        const std::uint32_t slot = pos & (HIT_RING_CAP - 1u);
+        sh.hitRing[slot] = make_uint4(id, hit.tri, __float_as_uint(hit.u), __float_as_uint(hit.v));
+        __threadfence_block();
+        *reinterpret_cast<volatile std::uint32_t*>(&sh.hitSeq[slot]) = pos / HIT_RING_CAP + 1u;
         return false;
     }
 };
+
+// The shading warp: rayColor:181-234 minus the traversals for 32 paths at a time, survivors appended to the
+// global ready ring (stream compaction), ended paths reported to ctl->live.
+template<int BLOCK>
+__device__ __forceinline__ void megaShadeLoop(
+    const FrameParams&  fp,
+    const SceneDevice&  scene,
+    const PathQueue     paths,
+    std::uint32_t*      meta,
+    float4*             radiance,
+    MegaControl*        ctl,
+    std::uint32_t*      ready,
+    const std::uint32_t log2Cap,
+    MegaShared<BLOCK>&  sh)
+{
+    const V3      sunDir = v3(fp.sky.sun_direction);
+    std::uint32_t head = 0, waited = 0;
+    while (true)
+    {
+        const std::uint32_t tail = *reinterpret_cast<volatile std::uint32_t*>(&sh.ringTail);
+        const std::uint32_t alive = *reinterpret_cast<volatile std::uint32_t*>(&sh.traversalAlive);
+        const std::uint32_t avail = tail - head;
+        if (avail == 0u)
+        {
+            if (alive == 0u) break;
+            __nanosleep(500);
+            continue;
+        }
+        if (avail < 32u && alive != 0u && waited < 16u)
+        {
+            // let the batch fill for up to ~8 us: a dense batch costs the same as a sparse one
+            ++waited;
+            __nanosleep(500);
+            continue;
+        }
+        waited = 0u;
+        const std::uint32_t n = min(avail, 32u);
+        const bool          mine = laneId() < n;
+        bool                survives = false, ended = false;
+        std::uint32_t       id = 0;
+        if (mine)
+        {
+            const std::uint32_t pos = head + laneId();
+            const std::uint32_t slot = pos & (HIT_RING_CAP - 1u);
+            while (*reinterpret_cast<volatile std::uint32_t*>(&sh.hitSeq[slot]) != pos / HIT_RING_CAP + 1u) {} // entry being written
+            __threadfence_block();
+            const uint4 e = sh.hitRing[slot];
+            id = e.x;
+            const HitRecord     hit{e.y, __uint_as_float(e.z), __uint_as_float(e.w), 0.0f};
+            const std::uint32_t m = __ldcg(meta + id);
+            const std::uint32_t bounce = m & META_BOUNCE_MASK;
+            const float4        oPix = ldcg4(paths.originPix + id);
+            const float4        thr = ldcg4(paths.throughput + id);
+            const std::uint32_t idx = __float_as_uint(oPix.w);
+            if (hit.tri == RF_NO_HIT)
+            {
+                const float4 dir = ldcg4(paths.direction + id);
+                const V3     sky = skyForMiss(fp, v3(dir.x, dir.y, dir.z), sunDir);
+                float4       rad = ldcg4(radiance + idx);
+                rad.x += thr.x * sky.x, rad.y += thr.y * sky.y, rad.z += thr.z * sky.z;
+                __stcg(radiance + idx, rad);
+                ended = true;
+            }
+            else
+            {
+                const SurfaceShade s = shadeSurfaceHit(fp, scene, hit, idx, v3(thr.x, thr.y, thr.z), sunDir);
+                __stcg(paths.originPix + id, make_float4(s.p.x, s.p.y, s.p.z, oPix.w));
+                __stcg(paths.direction + id, make_float4(s.wi.x, s.wi.y, s.wi.z, 0.0f));
+                __stcg(paths.throughput + id, make_float4(s.nextThroughput.x, s.nextThroughput.y, s.nextThroughput.z, 0.0f));
+                __stcg(paths.contribution + id, make_float4(s.contribution.x, s.contribution.y, s.contribution.z, 0.0f));
+                // every hit casts a shadow ray; the path goes on unless this was the last bounce (rayColor:205-207)
+                __stcg(meta + id, (bounce + 1u) | META_DO_SHADOW | (bounce < fp.numBounces ? META_DO_CLOSEST : 0u));
+                survives = true;
+            }
+        }
+        __syncwarp();
+        head += n;
+        if (laneId() == 0u) *reinterpret_cast<volatile std::uint32_t*>(&sh.ringHead) = head; // slots may be reused
+        const unsigned endedMask = __ballot_sync(0xFFFFFFFFu, ended);
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, survives);
+        if (mask != 0u)
+        {
+            const std::uint32_t count = static_cast<std::uint32_t>(__popc(mask));
+            std::uint32_t       pos = 0;
+            if (laneId() == 0u) pos = atomicAdd(&ctl->tail, count);
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            __threadfence(); // path state before its ring entry
+            if (survives)
+            {
+                const std::uint32_t at = pos + static_cast<std::uint32_t>(__popc(mask & ((1u << laneId()) - 1u)));
+                *reinterpret_cast<volatile std::uint32_t*>(ready + (at & ((1u << log2Cap) - 1u))) = ringEntry(at, log2Cap, id);
+            }
+            __threadfence();
+            __syncwarp();
+            if (laneId() == 0u) atomicAdd(&ctl->avail, static_cast<int>(count));
+        }
+        if (laneId() == 0u && endedMask != 0u) atomicSub(&ctl->live, static_cast<std::uint32_t>(__popc(endedMask)));
+    }
+}
 
 template<int VARIANT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_mega(
@@ -373,13 +380,33 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_mega(
     const std::uint32_t log2Cap,
     unsigned long long* stats)
 {
-    using IO = MegaIO<BLOCK>;
-    __shared__ typename IO::Shared sh;
+    using Shared = MegaShared<BLOCK>;
+    constexpr int TRAVERSAL_WARPS = Shared::WARPS - 1;
+    static_assert(TRAVERSAL_WARPS >= 1, "need at least one traversal warp and one shading warp");
+    __shared__ Shared sh;
     if (threadIdx.x < 6) sh.blockStats[threadIdx.x] = 0u;
-    if (threadIdx.x < IO::WARPS) sh.shadeCount[threadIdx.x] = 0u, sh.deadCount[threadIdx.x] = 0u, sh.starved[threadIdx.x] = 0u;
+    if (threadIdx.x < Shared::WARPS) sh.deadCount[threadIdx.x] = 0u, sh.starved[threadIdx.x] = 0u;
+    for (std::uint32_t i = threadIdx.x; i < HIT_RING_CAP; i += BLOCK) sh.hitSeq[i] = 0u;
+    if (threadIdx.x == 0) sh.ringTail = 0u, sh.ringHead = 0u, sh.traversalAlive = TRAVERSAL_WARPS;
     __syncthreads();
-    IO io{fp, scene, paths, meta, radiance, ctl, ready, log2Cap, sh};
-    traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
+    if (static_cast<int>(threadIdx.x >> 5) < TRAVERSAL_WARPS)
+    {
+        MegaIO<BLOCK> io{fp, scene, paths, meta, radiance, ctl, ready, log2Cap, sh};
+        traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
+        // paths ended by this warp that it has not reported yet (it may have left on the watchdog)
+        __syncwarp();
+        if (laneId() == 0u)
+        {
+            const std::uint32_t ended = atomicExch(&sh.deadCount[threadIdx.x >> 5], 0u);
+            if (ended != 0u) atomicSub(&ctl->live, ended);
+            __threadfence_block();
+            atomicSub(&sh.traversalAlive, 1u);
+        }
+    }
+    else
+    {
+        megaShadeLoop<BLOCK>(fp, scene, paths, meta, radiance, ctl, ready, log2Cap, sh);
+    }
     __syncthreads();
     if (threadIdx.x < 6 && sh.blockStats[threadIdx.x] != 0u)
     {
