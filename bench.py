@@ -292,7 +292,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     stage_stats = ren.stats()
     ren.set_stage_timing(False)
-    ren.set_pipeline(2)
+    ren.set_pipeline(-1)  # back to the automatic schedule
     barrier()
 
     # ---- end-to-end timing through the C-ABI with host buffers ----
@@ -354,12 +354,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "dtype": "f32", "data": "Sponza.pt baked from the reference's assets/Sponza.glb (deterministic asset, not synthetic)",
             "config": {"workload": workload_name(scene_name, w, h, bounces), "rays_per_step": rays_total // args.steps,
                        "paths_per_step": paths_total // args.steps, "l2": "flushed between timed iterations (256 MiB memset)",
-                       "pipeline": "2 tile sets on 2 CUDA streams, one launch per stage (raygen, 9 x trace, 8 x shade, accumulate per set)",
+                       "pipeline": (f"{stats['sub_frames']} tile set(s) on separate CUDA streams, one launch per stage (raygen, {bounces + 1} x trace, "
+                                    f"{bounces} x shade, accumulate per set)"
+                                    + (f"; each trace launch hands warps left with <= {stats['evict_max']} rays to a warp-per-ray tail launch"
+                                       if stats["evict_max"] else "")),
                        "partition": f"32x32 tiles, (tx+ty) % {world}, one NCCL sum-reduce of the HDR buffer per step" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": rays_total / e2e_seconds / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": w * h * 16, "ms_per_step": 1e3 * e2e_seconds / args.steps},
-            "gpu_launches": args.steps * 2 * (3 + 2 * bounces),
+            "gpu_launches": int(stats["kernel_launches"]),
             "roofline": roofline,
             "library": {"path": str(capi.LIB_PATH.relative_to(ROOT)), "build": capi.lib().rf_build_info().decode()},
         }

@@ -184,6 +184,9 @@ typedef struct rf_frame_stats
     double   device_ms_trace;      /* per-stage CUDA-event time, only filled when stage timing is on: the */
     double   device_ms_shade;      /* traversal launches (closest-hit + shadow rays), shading, the rest   */
     double   device_ms_other;
+    uint64_t kernel_launches;      /* kernels launched by rf_renderer_render since the last reset */
+    uint32_t sub_frames;           /* schedule in effect: tile sets per frame, */
+    uint32_t evict_max;            /* tail hand-over threshold (rf_renderer_set_pipeline / _set_tail_policy) */
 } rf_frame_stats;
 
 /* ---- the renderer: nlrs::ReferencePathTracer (pt/reference_path_tracer.hpp:59-102) ------------- */
@@ -249,12 +252,18 @@ rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled);
  * runs once `tri_min` lanes of a warp have a triangle pending, idle lanes are refilled once `refill_min`
  * are idle, `blocks_per_sm` persistent 256-thread blocks are launched per SM.  0 keeps a value. */
 rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refill_min, uint32_t blocks_per_sm);
-/* How a frame is scheduled (results never depend on it).  sub_frames (1..4, 0 keeps): the frame is traced as
- * that many independent tile sets on separate CUDA streams so one set's traversal tail overlaps the other's
- * work.  persistent_kernel (0/1, -1 keeps): experimental single-launch pipeline (csrc/mega.cuh) instead of one
+/* How a frame is scheduled (results never depend on it).  sub_frames (1..4, 0 keeps, -1 automatic = the default:
+ * 2 above ~0.6 M owned pixels, else 1): the frame is traced as that many independent tile sets on separate CUDA
+ * streams so one set's traversal tail overlaps the other's work.  persistent_kernel (0/1, -1 keeps): experimental single-launch pipeline (csrc/mega.cuh) instead of one
  * launch per stage.  variant (0..15, -1 keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling
  * variant and block size of the traversal kernel. */
 rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t persistent_kernel, int32_t variant, int32_t block_threads);
+/* Tail policy of the traversal launches (results never depend on it).  Once a launch's ray queue is dry, a warp left
+ * with <= evict_max rays writes their traversal state to a device buffer and exits; a small follow-up launch packs
+ * those stragglers densely and finishes them with node prefetching, so the SMs they pinned are free for the other
+ * tile sets' kernels.  0 = off (every ray ends on the lane it started on), -1 = automatic (the default: 8 when this
+ * GPU owns at most ~0.6 M pixels — launches that are mostly tail — else off), up to 32. */
+rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
 
 /* ---- the CPU traversal twin: nlrs::rayIntersectBvh (common/ray_intersection.hpp:43-49) --------- */
 

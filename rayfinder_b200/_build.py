@@ -38,7 +38,9 @@ def _newer(target: Path, sources: list[Path]) -> bool:
     return all(s.stat().st_mtime <= t for s in sources)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> Path:
+    if timeline:
+        return _build_timeline(verbose)
     headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "rayfinder_b200.h"]
     data = sorted(DATA.glob("*.bin"))
     sources = sorted(CSRC.glob("*.cpp")) + sorted(CSRC.glob("*.cu"))
@@ -68,5 +70,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def _build_timeline(verbose: bool, defines=(), suffix: str = "") -> Path:
+    """Instrumented debug build (per-warp timeline of the traversal launches, -DRF_TRACE_TIMELINE) next to the
+    product library: librayfinder_b200_timeline.so, selected with RAYFINDER_B200_LIB (tools/trace_timeline.py)."""
+    out = PKG / f"librayfinder_b200_timeline{suffix}.so"
+    OBJ.mkdir(exist_ok=True)
+    obj = OBJ / f"device.timeline{suffix}.o"
+    cmd = [NVCC, *NVCC_FLAGS, "-DRF_TRACE_TIMELINE", *[f"-D{d}" for d in defines], "-c", str(CSRC / "device.cu"), "-o", str(obj)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("timeline build failed")
+    objs = [str(obj)] + [str(OBJ / (src.name + ".o")) for src in sorted(CSRC.glob("*.cpp"))]
+    res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed")
+    return out
+
+
 if __name__ == "__main__":
+    if "--timeline" in sys.argv:
+        build()
+        defines = [a[2:] for a in sys.argv if a.startswith("-D")]
+        suffix = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--suffix=")), "")
+        print(_build_timeline(True, defines, suffix))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose=True))

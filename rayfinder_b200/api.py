@@ -364,6 +364,9 @@ class ReferencePathTracer:
     def set_pipeline(self, sub_frames: int = 0, persistent_kernel: int = -1, variant: int = -1, block_threads: int = 0) -> None:
         check(lib().rf_renderer_set_pipeline(self._handle, sub_frames, persistent_kernel, variant, block_threads))
 
+    def set_tail_policy(self, evict_max: int = -1) -> None:
+        check(lib().rf_renderer_set_tail_policy(self._handle, evict_max))
+
 
 class TraversalScene:
     """Device-resident (bvhNodes, triangles) for the GPU twin of ``rayIntersectBvh``."""

@@ -81,7 +81,8 @@ class FrameStats(C.Structure):
                 ("shadow_rays", C.c_uint64), ("closest_nodes_visited", C.c_uint64),
                 ("closest_triangles_tested", C.c_uint64), ("shadow_nodes_visited", C.c_uint64),
                 ("shadow_triangles_tested", C.c_uint64), ("device_ms_total", C.c_double),
-                ("device_ms_trace", C.c_double), ("device_ms_shade", C.c_double), ("device_ms_other", C.c_double)]
+                ("device_ms_trace", C.c_double), ("device_ms_shade", C.c_double), ("device_ms_other", C.c_double),
+                ("kernel_launches", C.c_uint64), ("sub_frames", C.c_uint32), ("evict_max", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/rayfinder_b200.h declares.
@@ -108,6 +109,7 @@ SIGNATURES = {
     "rf_renderer_set_stage_timing": (C.c_int32, [_P, C.c_int32]),
     "rf_renderer_set_tuning": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rf_renderer_set_pipeline": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "rf_renderer_set_tail_policy": (C.c_int32, [_P, C.c_int32]),
     "rf_traversal_scene_create": (C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(_P)]),
     "rf_traversal_scene_destroy": (None, [_P]),
     "rf_ray_intersect_bvh": (C.c_int32, [_P, _P, C.c_uint64, C.c_float, _P, _P, _P]),

@@ -170,9 +170,9 @@ rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std:
 template<int V, int BLOCK>
 void launchTraceV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& closestQueue,
                   const std::uint32_t* closestCount, HitRecord* hits, const PathQueue& shadowQueue, const std::uint32_t* shadowCount,
-                  float4* radiance, std::uint32_t* cursor, unsigned long long* stats)
+                  float4* radiance, std::uint32_t* cursor, const StragglerBuffer& stragglers, unsigned long long* stats)
 {
-    k_trace<V, BLOCK><<<grid, BLOCK, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stats);
+    k_trace<V, BLOCK><<<grid, BLOCK, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stragglers, stats);
 }
 template<typename... Args>
 void launchTrace(int variant, int block, Args&&... args)
@@ -251,6 +251,7 @@ struct rf_renderer
         DeviceBuffer<HitRecord>     hits;
         DeviceBuffer<std::uint32_t> ownedTiles;
         DeviceBuffer<std::uint32_t> counters; // see counterSlots()
+        DeviceBuffer<StragglerRecord> stragglers; // rays handed over by the tails of the traversal launches (traversal.cuh)
         DeviceBuffer<std::uint32_t> meta, ready; // persistent-kernel mode: path meta, ready ring (mega.cuh)
         DeviceBuffer<MegaControl>   control;
         std::uint32_t               log2Cap = 0;
@@ -260,7 +261,9 @@ struct rf_renderer
     };
     static constexpr int MAX_SUBFRAMES = 4;
     SubFrame    sub[MAX_SUBFRAMES];
-    int         numSubFrames = 2;
+    std::uint64_t kernelLaunches = 0;   // kernels launched by render() since the last reset_stats
+    int         numSubFrames = 2;       // in effect (updateTiles)
+    int         requestedSubFrames = 0; // 0: automatic
     bool        megakernel = false; // experimental: the frame as one persistent kernel (mega.cuh); slower so far
     cudaEvent_t forkEvent = nullptr;
 
@@ -344,6 +347,13 @@ struct rf_renderer
                 }
                 msTrace += span(e, e + 1);
                 msOther += span(e + 1, e + 2);
+                if (std::getenv("RF_DEBUG_STAGES"))
+                {
+                    // per-launch spans of one frame: raygen, then (trace, shade) per bounce, last trace, accumulate
+                    std::fprintf(stderr, "[stages] total %.3f:", ms);
+                    for (std::uint32_t k = 0; k + 1 < t.stagesUsed; ++k) std::fprintf(stderr, " %.3f", span(k, k + 1));
+                    std::fprintf(stderr, "\n");
+                }
             }
             t.stagesUsed = 0;
             eventPool.push_back(std::move(t));
@@ -379,6 +389,11 @@ struct rf_renderer
         const std::uint32_t tilesY = (params.framebuffer_height + TILE - 1) / TILE;
         std::vector<std::uint32_t> owned[MAX_SUBFRAMES];
         std::uint32_t              k = 0;
+        ownedTileCount = 0;
+        for (std::uint32_t ty = 0; ty < tilesY; ++ty)
+            for (std::uint32_t tx = 0; tx < tilesX; ++tx)
+                if ((tx + ty) % world == rank) ++ownedTileCount;
+        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : (smallFrame() ? 1 : 2);
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) owned[k++ % static_cast<std::uint32_t>(numSubFrames)].push_back(ty * tilesX + tx);
@@ -396,6 +411,7 @@ struct rf_renderer
                 RF_CUDA(sf.hits.allocate(need));
                 RF_CUDA(sf.ownedTiles.allocate(sf.numOwnedTiles));
                 if (!sf.counters.ptr) RF_CUDA(sf.counters.allocate(counterSlots(1024)));
+                if (!sf.stragglers.ptr) RF_CUDA(sf.stragglers.allocate(stragglerCapacity()));
                 if (!sf.control.ptr) RF_CUDA(sf.control.allocate(1));
                 sf.log2Cap = 0;
                 while ((1ull << sf.log2Cap) < need) ++sf.log2Cap;
@@ -419,6 +435,17 @@ struct rf_renderer
     int traceBlocksPerSm = 4; // in units of 256 threads: x <= 64 registers, 32 KB of shared stack
     int traceBlock = 256;     // threads per traversal block (64, 128 or 256)
     int gridFor(int blocksPerSm) const { return numSms * blocksPerSm; }
+    // Tail policy of the traversal launches: warps left with <= evictMax rays once the queue is dry hand them to a
+    // small follow-up launch (0 = off).  On by default when the frame runs as several tile sets, where the SMs a
+    // tail frees are used by the other sets.
+    // Automatic scheduling, from measurements on B200 (Sponza, 8 bounces; DESIGN.md "Tails"): with more than ~0.6 M
+    // paths per GPU (the 1080p frame on 1-2 GPUs) two tile sets on two streams and no hand-over are fastest; below
+    // that (a 1080p frame split over 4-8 GPUs) a launch is mostly tail and one tile set with the hand-over wins.
+    int           evictMax = -1; // -1: automatic
+    std::uint32_t ownedTileCount = 0;
+    bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
+    std::uint32_t stragglerCapacity() const { return static_cast<std::uint32_t>(numSms) * 64u * 8u; }
+    std::uint32_t effectiveEvictMax() const { return evictMax >= 0 ? static_cast<std::uint32_t>(evictMax) : (smallFrame() ? 8u : 0u); }
 };
 
 extern "C" rf_status rf_renderer_create(
@@ -474,7 +501,9 @@ extern "C" rf_status rf_renderer_create(
         RF_CUDA(rawTris.allocate(numTris * 12));
         RF_CUDA(cudaMemcpy(rawNodes.ptr, scene->bvh_nodes, numNodes * sizeof(rf_bvh_node), cudaMemcpyHostToDevice));
         RF_CUDA(cudaMemcpy(rawTris.ptr, scene->position_attributes, numTris * sizeof(rf_position_attribute), cudaMemcpyHostToDevice));
-        RF_CUDA(r->nodes.allocate(numNodes));
+        // + 64 zeroed records: the tail kernel reads 32-node windows that may run past the last node (straggler.cuh)
+        RF_CUDA(r->nodes.allocate(numNodes + 64));
+        RF_CUDA(cudaMemset(r->nodes.ptr, 0, (numNodes + 64) * sizeof(PackedNode)));
         RF_CUDA(r->tris.allocate(3 * numTris));
         k_pack_nodes<<<r->numSms * 4, 256>>>(rawNodes.ptr, numNodes, r->nodes.ptr);
         k_pack_triangles<<<r->numSms * 4, 256>>>(rawTris.ptr, 4, numTris, r->tris.ptr);
@@ -520,7 +549,7 @@ extern "C" rf_status rf_renderer_create(
         RF_CUDA(cudaEventCreateWithFlags(&r->sub[i].done, cudaEventDisableTiming));
     }
     if (const char* e = std::getenv("RF_MEGAKERNEL")) r->megakernel = std::atoi(e) != 0;
-    if (const char* e = std::getenv("RF_SUBFRAMES")) r->numSubFrames = std::min(std::max(std::atoi(e), 1), static_cast<int>(rf_renderer::MAX_SUBFRAMES));
+    if (const char* e = std::getenv("RF_SUBFRAMES")) r->requestedSubFrames = std::min(std::max(std::atoi(e), 0), static_cast<int>(rf_renderer::MAX_SUBFRAMES));
 
     st = r->applyParams(desc->render_params);
     if (st != RF_OK) return st;
@@ -639,6 +668,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             launchMega(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], sf.meta.ptr, r->radiance.ptr, sf.control.ptr, sf.ready.ptr,
                        sf.log2Cap, r->stats.ptr);
             k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+            r->kernelLaunches += 4;
             if (std::getenv("RF_DEBUG_MEGA"))
             {
                 MegaControl   c{};
@@ -657,10 +687,24 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             continue;
         }
 
+        // Straggler hand-over of the k-th traversal launch (off in the staged timing mode: one launch per stage).
+        const std::uint32_t evictMax = staged ? 0u : r->effectiveEvictMax();
+        std::uint32_t* const stragglerCounts = ctr + 2u * fp.numBounces + 2u;
+        std::uint32_t* const stragglerCursors = ctr + 3u * fp.numBounces + 3u;
+        const auto           stragglersOf = [&](std::uint32_t k) { return StragglerBuffer{sf.stragglers.ptr, &stragglerCounts[k], r->stragglerCapacity(), evictMax}; };
+        const auto           finishStragglers = [&](std::uint32_t k, const PathQueue& closestQueue, const PathQueue& shadowQueue) {
+            if (evictMax == 0u) return;
+            // persistent warps, one ray at a time each; blocks beyond the number of records exit at once
+            k_trace_stragglers<<<r->numSms * STRAGGLER_WARPS_PER_SM / STRAGGLER_WARPS_PER_BLOCK, STRAGGLER_BLOCK_THREADS, 0, ss>>>(
+                sfp, scene, closestQueue, sf.hits.ptr, shadowQueue, r->radiance.ptr, &stragglerCursors[k], stragglersOf(k), r->stats.ptr);
+        };
+
         k_raygen<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
         // closest-hit rays of bounce 1
-        launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0], r->stats.ptr);
+        launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0],
+                    stragglersOf(0), r->stats.ptr);
+        finishStragglers(0, sf.queues[0], sf.queues[0]);
         for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
         {
             const int in = (bounce - 1) & 1, outQ = bounce & 1;
@@ -670,10 +714,13 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             // shadow rays of this bounce + closest-hit rays of the next one (none after the last bounce)
             const bool last = bounce == fp.numBounces;
             launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
-                        r->radiance.ptr, &cursors[bounce], r->stats.ptr);
+                        r->radiance.ptr, &cursors[bounce], stragglersOf(bounce), r->stats.ptr);
+            finishStragglers(bounce, sf.queues[outQ], sf.queues[outQ]);
         }
         RF_CUDA(stageMark());
         k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+        // raygen + (numBounces + 1) traversal launches (+ their straggler follow-ups) + numBounces shades + accumulate
+        r->kernelLaunches += 2ull + (fp.numBounces + 1ull) * (evictMax != 0u ? 2ull : 1ull) + fp.numBounces;
         RF_CUDA(stageMark());
         if (i > 0)
         {
@@ -783,6 +830,9 @@ extern "C" rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out)
     out->device_ms_trace = r->msTrace;
     out->device_ms_shade = r->msShade;
     out->device_ms_other = r->msOther;
+    out->kernel_launches = r->kernelLaunches;
+    out->sub_frames = static_cast<std::uint32_t>(r->numSubFrames);
+    out->evict_max = r->megakernel ? 0u : r->effectiveEvictMax();
     return RF_OK;
 }
 
@@ -794,6 +844,7 @@ extern "C" rf_status rf_renderer_reset_stats(rf_renderer* r)
     r->drainTimings(true);
     RF_CUDA(cudaMemset(r->stats.ptr, 0, STAT_COUNT * sizeof(unsigned long long)));
     r->frames = 0;
+    r->kernelLaunches = 0;
     r->totalMs = r->msTrace = r->msShade = r->msOther = 0.0;
     return RF_OK;
 }
@@ -815,12 +866,46 @@ extern "C" rf_status rf_renderer_set_tuning(rf_renderer* r, std::uint32_t triMin
     return RF_OK;
 }
 
+#ifdef RF_TRACE_TIMELINE
+// Debug build only: arm the per-warp timeline of the traversal launches / read it back (tools/trace_timeline.py).
+extern "C" int rf_debug_timeline_arm(std::uint32_t capacity)
+{
+    static TimelineRecord* buf = nullptr;
+    if (buf) cudaFree(buf);
+    if (cudaMalloc(&buf, sizeof(TimelineRecord) * capacity) != cudaSuccess) return 1;
+    const std::uint32_t zero = 0;
+    cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_timelineCount, &zero, sizeof(zero));
+    cudaMemcpyToSymbol(g_timelineCap, &capacity, sizeof(capacity));
+    return cudaDeviceSynchronize() != cudaSuccess;
+}
+extern "C" std::uint32_t rf_debug_timeline_read(void* dst, std::uint32_t capacity)
+{
+    cudaDeviceSynchronize();
+    std::uint32_t   n = 0;
+    TimelineRecord* buf = nullptr;
+    cudaMemcpyFromSymbol(&n, g_timelineCount, sizeof(n));
+    cudaMemcpyFromSymbol(&buf, g_timeline, sizeof(buf));
+    n = std::min(n, capacity);
+    if (buf && n) cudaMemcpy(dst, buf, sizeof(TimelineRecord) * n, cudaMemcpyDeviceToHost);
+    return n;
+}
+#endif
+
+extern "C" rf_status rf_renderer_set_tail_policy(rf_renderer* r, std::int32_t evictMax)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tail_policy: null renderer");
+    if (evictMax > 32) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tail_policy: value out of range");
+    r->evictMax = evictMax < 0 ? -1 : evictMax;
+    return RF_OK;
+}
+
 extern "C" rf_status rf_renderer_set_pipeline(rf_renderer* r, std::int32_t subFrames, std::int32_t persistentKernel, std::int32_t variant, std::int32_t blockThreads)
 {
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_pipeline: null renderer");
     if (subFrames > rf_renderer::MAX_SUBFRAMES || variant > 15 || (blockThreads != 0 && blockThreads != 64 && blockThreads != 128 && blockThreads != 256))
         return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_pipeline: value out of range");
-    if (subFrames > 0 && subFrames != r->numSubFrames) r->numSubFrames = subFrames, r->tilesDirty = true;
+    if (subFrames != 0 && (subFrames < 0 ? 0 : subFrames) != r->requestedSubFrames) r->requestedSubFrames = subFrames < 0 ? 0 : subFrames, r->tilesDirty = true;
     if (persistentKernel >= 0) r->megakernel = persistentKernel != 0;
     if (variant >= 0) r->variant = variant;
     if (blockThreads > 0) r->traceBlock = blockThreads;

@@ -12,6 +12,7 @@
 #pragma once
 
 #include "rf_internal.h"
+#include "straggler.cuh"
 #include "traversal.cuh"
 
 namespace rfb200
@@ -64,7 +65,9 @@ struct SceneDevice
 //   [b]                       b = 0..numBounces: entries of the queue produced for bounce b + 1
 //                             ([0] = primary rays from k_raygen, [b] = hits appended by k_shade of bounce b)
 //   [numBounces + 1 + k]      work-fetch cursor of the k-th traversal launch of the frame
-__host__ __device__ inline std::uint32_t counterSlots(std::uint32_t numBounces) { return 2u * numBounces + 4u; }
+//   [2 numBounces + 2 + k]    straggler records appended by the k-th traversal launch
+//   [3 numBounces + 3 + k]    work-fetch cursor of its follow-up launch (k_trace_stragglers)
+__host__ __device__ inline std::uint32_t counterSlots(std::uint32_t numBounces) { return 4u * numBounces + 4u; }
 
 enum StatSlot
 {
@@ -353,6 +356,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
 // 9 traversal launches per 8-bounce frame instead of 16, and one kernel tail instead of two.
 struct TraceIO : CursorSource
 {
+    static constexpr bool HANDS_OVER_STRAGGLERS = true; // at run time: stragglers.evictMax != 0
+    const StragglerBuffer stragglers;
     const FrameParams&  fp;
     const SceneDevice&  scene;
     const PathQueue     closestQueue;
@@ -420,6 +425,7 @@ __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_tr
     const std::uint32_t* __restrict__ shadowCount,  // nullptr: no shadow rays in this launch
     float4*              radiance,
     std::uint32_t*       fetchCursor,
+    const StragglerBuffer stragglers,               // evictMax == 0: every ray ends in this launch
     unsigned long long*  stats)
 {
     __shared__ std::uint32_t blockStats[6];
@@ -427,9 +433,61 @@ __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_tr
     __syncthreads();
     const std::uint32_t numClosest = closestCount ? *closestCount : 0u;
     const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
-    TraceIO             io{{fetchCursor, numClosest + numShadow}, fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance,
-               v3(fp.sky.sun_direction), blockStats};
+    TraceIO io{{fetchCursor, numClosest + numShadow}, stragglers, fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance,
+                  v3(fp.sky.sun_direction), blockStats};
     traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
+    __syncthreads();
+    if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
+    {
+        const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};
+        atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(blockStats[threadIdx.x]));
+    }
+}
+
+// The follow-up of a k_trace launch that handed over its stragglers: one WARP per ray (straggler.cuh) — the warp
+// loads 32 consecutive nodes per memory round trip, tests them lane-parallel and walks the ray through the
+// results, ~3x faster per ray than a lone lane of the persistent loop.  Warps take records one at a time.
+constexpr int STRAGGLER_BLOCK_THREADS = STRAGGLER_WARPS_PER_BLOCK * 32;
+__global__ void __launch_bounds__(STRAGGLER_BLOCK_THREADS) k_trace_stragglers(
+    const FrameParams     fp,
+    const SceneDevice     scene,
+    const PathQueue       closestQueue,
+    HitRecord*            hits,
+    const PathQueue       shadowQueue,
+    float4*               radiance,
+    std::uint32_t*        fetchCursor,
+    const StragglerBuffer stragglers,
+    unsigned long long*   stats)
+{
+    __shared__ std::uint32_t       blockStats[6];
+    __shared__ StragglerWarpShared warpShared[STRAGGLER_WARPS_PER_BLOCK];
+    const std::uint32_t numRecords = min(*stragglers.count, stragglers.capacity);
+    if (blockIdx.x * STRAGGLER_WARPS_PER_BLOCK >= numRecords) return; // more warps than rays: nothing for this block
+    if (threadIdx.x < 6) blockStats[threadIdx.x] = 0u;
+    __syncthreads();
+    TraceIO io{{fetchCursor, numRecords}, stragglers, fp, scene, closestQueue, 0u, hits, shadowQueue, radiance, v3(fp.sky.sun_direction), blockStats};
+#ifdef RF_TRACE_TIMELINE
+    const unsigned long long tlStart = globalTimerNs();
+    std::uint32_t            tlRays = 0;
+#endif
+    while (true)
+    {
+        std::uint32_t idx = 0;
+        if (laneId() == 0u) idx = atomicAdd(fetchCursor, 1u);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= numRecords) break;
+        traceStragglerWarp(scene.nodes, scene.tris, stragglers.records + idx, warpShared[threadIdx.x >> 5], io);
+#ifdef RF_TRACE_TIMELINE
+        ++tlRays;
+#endif
+    }
+#ifdef RF_TRACE_TIMELINE
+    if (laneId() == 0u && g_timeline != nullptr)
+    {
+        const std::uint32_t at = atomicAdd(&g_timelineCount, 1u);
+        if (at < g_timelineCap) g_timeline[at] = TimelineRecord{io.timelineTag(), tlStart, tlStart, globalTimerNs(), tlRays, 0u, 0u, 0u};
+    }
+#endif
     __syncthreads();
     if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
     {

@@ -121,6 +121,10 @@ template<int BLOCK>
 struct MegaIO
 {
     using Shared = MegaShared<BLOCK>;
+    static constexpr bool HANDS_OVER_STRAGGLERS = false; // rays end on the lane they started on (traversal.cuh)
+#ifdef RF_TRACE_TIMELINE
+    __device__ __forceinline__ unsigned long long timelineTag() const { return 0ull; }
+#endif
     const FrameParams& fp;
     const SceneDevice& scene;
     const PathQueue    paths; // path state, indexed by path id

@@ -57,9 +57,32 @@ struct __align__(16) HitRecord
     float         u, v, t;
 };
 
+// A ray taken off its lane in the middle of its traversal (see "stragglers" below): everything needed to go on
+// with it on another lane, bit for bit.  208 bytes, written and read as 13 x 16 B.
+struct __align__(16) StragglerRecord
+{
+    uint4 head[5];  // (rayIdx, flags, cur, pendTri) (pendEnd, rayNodes, rayTris, tmax) (o.xyz, d.x) (d.yz, hit.tri, hit.u) (hit.v, hit.t, -, -)
+    uint4 stack[8]; // the 32 stack entries, bottom first (only the first `depth` are meaningful)
+};
+static_assert(sizeof(StragglerRecord) == 208, "13 x 16 B");
+
+struct StragglerBuffer
+{
+    StragglerRecord* records;
+    std::uint32_t*   count;    // records appended so far (may overshoot `capacity` transiently; readers clamp)
+    std::uint32_t    capacity;
+    std::uint32_t    evictMax; // a warp hands its rays over once the queue is dry and it has <= evictMax of them left (0: never)
+};
+
 // Work source over a plain array of `numRays` items: a device cursor advanced with one atomicAdd per warp.
 struct CursorSource
 {
+    // Straggler policy of the IO (compile time): false = every ray ends on the lane it started on; true = once the
+    // queue is dry, warps with few rays left append them to `stragglers` and exit (the IO then has that member).
+    static constexpr bool HANDS_OVER_STRAGGLERS = false;
+#ifdef RF_TRACE_TIMELINE
+    __device__ __forceinline__ unsigned long long timelineTag() const { return reinterpret_cast<unsigned long long>(cursor); }
+#endif
     std::uint32_t* cursor;
     std::uint32_t  numRays;
     __device__ __forceinline__ std::uint32_t acquire(const std::uint32_t want, bool, std::uint32_t& base, bool& exhausted) const
@@ -205,6 +228,25 @@ __device__ __forceinline__ std::uint32_t stackLoad(const std::uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(addr) : "memory");
     return value;
 }
+
+#ifdef RF_TRACE_TIMELINE
+// Debug build only (python -m rayfinder_b200._build --timeline): every warp of a traversal launch appends
+// (launch tag, start, queue-dry, exit, rays, node-step rounds) in %globaltimer ns; tools/trace_timeline.py reads them.
+struct TimelineRecord
+{
+    unsigned long long tag, start, dry, exit;
+    std::uint32_t      rays, rounds, sm, pad;
+};
+__device__ TimelineRecord* g_timeline;
+__device__ std::uint32_t   g_timelineCount;
+__device__ std::uint32_t   g_timelineCap;
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 
 // The persistent traversal loop.  IO supplies the rays and consumes the results:
 //   uint32 IO::acquire(want, mayWait, base, exhausted)   warp-uniform: reserve up to `want` work items, return
@@ -392,8 +434,37 @@ __device__ __forceinline__ void traceRays(
         }
     };
 
+    // ---- stragglers ------------------------------------------------------------------------------------
+    // The last rays of a launch walk their ~10^3 nodes one dependent load after the other while the rest of the
+    // machine idles, and each of them pins a whole block (registers, 32 KB of stack) to its SM.  With
+    // IO::HANDS_OVER_STRAGGLERS a warp that is left with a few rays once the queue is dry writes their complete
+    // traversal state to a device buffer and exits; a follow-up launch gives each of those rays a whole warp
+    // (straggler.cuh), which walks it ~2.5x faster than a lone lane can.  The state is restored bit for bit:
+    // results and counters do not change.
+    const auto evictRay = [&](StragglerRecord* rec) {
+        const std::uint32_t depth = (stackTop - stackBase) / STACK_STRIDE;
+        const std::uint32_t flags = static_cast<std::uint32_t>(state) | (laneAnyHit ? 0x100u : 0u) | (depth << 16);
+        rec->head[0] = make_uint4(rayIdx, flags, cur, pendTri);
+        rec->head[1] = make_uint4(pendEnd, rayNodes, rayTris, __float_as_uint(tmax));
+        rec->head[2] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+        rec->head[3] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), hit.tri, __float_as_uint(hit.u));
+        rec->head[4] = make_uint4(__float_as_uint(hit.v), __float_as_uint(hit.t), 0u, 0u);
+        std::uint32_t* entries = reinterpret_cast<std::uint32_t*>(rec->stack);
+        for (std::uint32_t k = 0; k < depth; ++k) entries[k] = stackLoad(stackBase + k * STACK_STRIDE);
+    };
+    bool mayEvict = IO::HANDS_OVER_STRAGGLERS;
+#ifdef RF_TRACE_TIMELINE
+    const unsigned long long tlStart = globalTimerNs();
+    unsigned long long       tlDry = 0;
+    std::uint32_t            tlRays = 0, tlRounds = 0, tlMaxNodes = 0;
+#endif
+
     while (true)
     {
+#ifdef RF_TRACE_TIMELINE
+        ++tlRounds;
+        if (exhausted && tlDry == 0) tlDry = globalTimerNs();
+#endif
         // ---- node steps: one BVH node per lane in NODE state ------------------------------------------
 #pragma unroll
         for (int k = 0; k < NODE_STEPS_PER_VOTE; ++k)
@@ -446,6 +517,9 @@ __device__ __forceinline__ void traceRays(
         if ((nodeMask | triMask) == 0xFFFFFFFFu) continue;
         if (state == DONE)
         {
+#ifdef RF_TRACE_TIMELINE
+            tlMaxNodes = max(tlMaxNodes, rayNodes + (rayTris << 16));
+#endif
             if (io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes, rayTris, RF_ANY_HIT, o, d, tmax, laneAnyHit))
                 startRay(); // chained ray (e.g. the closest-hit ray of a path right after its shadow ray)
             else
@@ -459,6 +533,9 @@ __device__ __forceinline__ void traceRays(
             std::uint32_t       base = 0;
             const std::uint32_t granted = io.acquire(idleCount, busyMask == 0u, base, exhausted);
             gotWork = granted != 0u;
+#ifdef RF_TRACE_TIMELINE
+            tlRays += granted;
+#endif
             if (state == IDLE)
             {
                 const std::uint32_t rank = static_cast<std::uint32_t>(__popc(~busyMask & ((1u << laneId()) - 1u)));
@@ -471,7 +548,40 @@ __device__ __forceinline__ void traceRays(
             }
         }
         if (exhausted && busyMask == 0u && !gotWork) break;
+        if constexpr (IO::HANDS_OVER_STRAGGLERS)
+        {
+          if (mayEvict && exhausted && !gotWork)
+          {
+            const std::uint32_t busy = static_cast<std::uint32_t>(__popc(busyMask));
+            if (busy <= io.stragglers.evictMax)
+            {
+                std::uint32_t base = 0;
+                if (laneId() == 0u) base = atomicAdd(io.stragglers.count, busy);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + busy <= io.stragglers.capacity)
+                {
+                    if (state != IDLE) evictRay(io.stragglers.records + base + static_cast<std::uint32_t>(__popc(busyMask & ((1u << laneId()) - 1u))));
+                    break;
+                }
+                // Buffer full: the rays end here.  The slots this warp reserved below `capacity` are marked empty
+                // (flags 0 = IDLE), so the reader does not take what an earlier launch left there for a ray.
+                if (laneId() < busy && base + laneId() < io.stragglers.capacity) io.stragglers.records[base + laneId()].head[0] = make_uint4(0u, 0u, 0u, 0u);
+                mayEvict = false;
+            }
+          }
+        }
     }
+#ifdef RF_TRACE_TIMELINE
+    tlMaxNodes = __reduce_max_sync(0xFFFFFFFFu, tlMaxNodes & 0xFFFFu) | (__reduce_max_sync(0xFFFFFFFFu, tlMaxNodes >> 16) << 16);
+    if (laneId() == 0u && g_timeline != nullptr)
+    {
+        const std::uint32_t at = atomicAdd(&g_timelineCount, 1u);
+        std::uint32_t       sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        if (at < g_timelineCap)
+            g_timeline[at] = TimelineRecord{io.timelineTag(), tlStart, tlDry, globalTimerNs(), tlRays, tlRounds, sm, tlMaxNodes};
+    }
+#endif
 #undef RF_ANY_HIT
 }
 

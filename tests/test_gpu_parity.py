@@ -304,24 +304,56 @@ def test_texture_limit_error_message(duck_pt):
     assert str(e.value) == f"Texture buffer size ({huge.size * 4}) exceeds maxStorageBufferBindingSize ({1 << 30})."
 
 
-@pytest.mark.parametrize("sub_frames,persistent,variant,block,tri_min,refill_min", [
-    (1, 0, 3, 256, 4, 4), (2, 0, 3, 256, 4, 4), (4, 0, 2, 64, 1, 1), (3, 0, 1, 128, 32, 32), (1, 0, 11, 256, 8, 16),
-    (1, 1, 3, 256, 4, 4), (2, 1, 3, 128, 2, 8)])
-def test_results_do_not_depend_on_scheduling(duck_pt, sub_frames, persistent, variant, block, tri_min, refill_min):
-    """Sub-frame pipelining, the experimental persistent kernel, the compile-time scheduling variants, block sizes and
-    the run-time knobs change how warps are kept busy — never a counter or a pixel."""
+@pytest.mark.parametrize("sub_frames,persistent,variant,block,tri_min,refill_min,evict_max", [
+    (1, 0, 3, 256, 4, 4, 0), (2, 0, 3, 256, 4, 4, -1), (4, 0, 2, 64, 1, 1, 8), (3, 0, 1, 128, 32, 32, 32), (1, 0, 11, 256, 8, 16, 1),
+    (1, 0, 3, 256, 4, 4, 32), (2, 0, 3, 256, 4, 4, 0), (1, 1, 3, 256, 4, 4, -1), (2, 1, 3, 128, 2, 8, -1)])
+def test_results_do_not_depend_on_scheduling(duck_pt, sub_frames, persistent, variant, block, tri_min, refill_min, evict_max):
+    """Sub-frame pipelining, the experimental persistent kernel, the compile-time scheduling variants, block sizes,
+    the run-time knobs and the straggler hand-over (rays moved to another lane in mid-traversal) change how warps are
+    kept busy — never a counter or a pixel."""
     w, h, spp, bounces = 150, 70, 2, 5
     cam = rf.bvh_visualizer_camera(duck_pt.bvh_nodes, w, h)
     ren, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
     ren.set_pipeline(1, 0, 3, 256)
+    ren.set_tail_policy(0)
     ren.render(), ren.render()
     ref_img, _ = ren.read_hdr()
     ref_stats = ren.stats()
     ren2, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
     ren2.set_tuning(tri_min, refill_min, 4)
     ren2.set_pipeline(sub_frames, persistent, variant, block)
+    ren2.set_tail_policy(evict_max)
     ren2.render(), ren2.render()
     img, _ = ren2.read_hdr()
     for key in O.COUNTER_NAMES:
         assert ren2.stats()[key] == ref_stats[key], key
+    assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evict_max,sub_frames", [(1, 1), (8, 1), (32, 2), (-1, -1)])
+def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames):
+    """The warp-per-ray tail kernel (csrc/straggler.cuh: 32-node windows, lane-parallel slab and first-triangle tests,
+    one triangle per lane in multi-triangle leaves) resumes rays in mid-traversal.  On Sponza's long grazing rays —
+    including the 1/256 of the shadow rays that are axis-parallel and take the NaN re-test — every counter and
+    every pixel equals the run in which each ray ends on the lane it started on."""
+    w, h, bounces = 480, 270, 8
+    cam = rf.fly_camera(w, h)
+    ren, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+    ren.set_pipeline(1, 0, 3, 256)
+    ren.set_tail_policy(0)
+    ren.render(), ren.render()
+    ref_img, _ = ren.read_hdr()
+    ref_stats = ren.stats()
+    assert ref_stats["evict_max"] == 0 and ref_stats["sub_frames"] == 1
+    ren2, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+    ren2.set_pipeline(sub_frames, 0, 3, 256)
+    ren2.set_tail_policy(evict_max)
+    ren2.render(), ren2.render()
+    img, _ = ren2.read_hdr()
+    stats = ren2.stats()
+    assert stats["evict_max"] == (8 if evict_max < 0 else evict_max)  # automatic: a small frame hands its tails over
+    assert stats["kernel_launches"] > ref_stats["kernel_launches"]
+    for key in O.COUNTER_NAMES:
+        assert stats[key] == ref_stats[key], key
     assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))

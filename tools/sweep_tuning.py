@@ -31,6 +31,7 @@ def main():
     for mega, bs, sort, variant, blocks, tri, refill in itertools.product(mega_list, bs_list, sort_list, variant_list, blocks_list, tri_list, refill_list):
         ren.set_tuning(tri, refill, blocks)
         ren.set_pipeline(sort + 1, mega, variant, bs)
+        ren.set_tail_policy(int(os.environ.get('RF_EVICT_MAX', -1)))
         for k in range(frames + 1):
             if k == 1:
                 ren.reset_stats()
