@@ -2,7 +2,7 @@
 """Per-warp timeline of the traversal launches of one frame (GPU box, instrumented debug build).
 
     python -m rayfinder_b200._build --timeline
-    RAYFINDER_B200_LIB=rayfinder_b200/librayfinder_b200_timeline.so python tools/trace_timeline.py [WxH] [sub_frames] [evict_max]
+    RAYFINDER_B200_LIB=rayfinder_b200/librayfinder_b200_timeline.so python tools/trace_timeline.py [WxH] [sub_frames] [evict_max] [persistent_kernel]
 
 For every traversal launch: when the first / last warp started, when the ray queue ran dry (first / last warp to
 notice), when the warps exited (percentiles), and how many warps were still running at points of the tail.
@@ -29,6 +29,7 @@ def main():
     size = sys.argv[1] if len(sys.argv) > 1 else "672x384"
     sub = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     evict = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    mega = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     w, h = (int(x) for x in size.split("x"))
     lib = capi.lib()
     raw = C.CDLL(str(capi.LIB_PATH))
@@ -38,7 +39,7 @@ def main():
     pt = rfa.load_scene("Sponza")
     params = rf.RenderParameters((w, h), rf.fly_camera(w, h), rf.SamplingParams(1, 8), rf.Sky(), 0.25)
     ren = rf.ReferencePathTracer(params, (w, h), rf.SceneArrays.from_pt(pt))
-    ren.set_pipeline(sub, 0, 3, 256)
+    ren.set_pipeline(sub, mega, 3, 256)
     ren.set_tail_policy(evict)
     for k in range(3):
         params.exposure = 0.25 + 0.01 * k
