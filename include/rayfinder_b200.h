@@ -331,6 +331,20 @@ rf_status rf_build_bvh(
     uint64_t*           out_num_nodes,
     uint64_t*           out_triangle_indices);
 
+/* buildBvh on the GPU (csrc/bvh_build.cu): same arguments and byte-identical results as
+ * rf_build_bvh — nodes, padding words and triangleIndices — built level by level with data-parallel kernels
+ * (atomic box reductions, binned SAH sweep per node, std::partition reproduced with one scan).  `device` < 0 selects
+ * the current CUDA device; `out_device_ms` (may be NULL) receives the device time of the build without the
+ * host<->device copies.  Fails with RF_ERROR_CUDA when there is no CUDA device (rf_build_bvh is the host builder). */
+rf_status rf_build_bvh_device(
+    const rf_positions* triangles,
+    uint64_t            num_triangles,
+    int32_t             device,
+    rf_bvh_node*        out_nodes,
+    uint64_t*           out_num_nodes,
+    uint64_t*           out_triangle_indices,
+    float*              out_device_ms);
+
 /* ---- .pt container: nlrs::PtFormat + serialize/deserialize (pt-format/pt_format.hpp:18-43) ----- */
 
 typedef struct rf_pt_file rf_pt_file;

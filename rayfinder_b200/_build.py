@@ -82,7 +82,7 @@ def _build_timeline(verbose: bool, defines=(), suffix: str = "") -> Path:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("timeline build failed")
-    objs = [str(obj)] + [str(OBJ / (src.name + ".o")) for src in sorted(CSRC.glob("*.cpp"))]
+    objs = [str(obj)] + [str(OBJ / (src.name + ".o")) for src in sorted(CSRC.glob("*.cpp")) + sorted(CSRC.glob("*.cu")) if src.name != "device.cu"]
     res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

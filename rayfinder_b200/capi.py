@@ -117,6 +117,7 @@ SIGNATURES = {
     "rf_create_camera": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]),
     "rf_sky_state_new": (C.c_int32, [C.POINTER(Sky), C.POINTER(SkyState)]),
     "rf_build_bvh": (C.c_int32, [_P, C.c_uint64, _P, C.POINTER(C.c_uint64), _P]),
+    "rf_build_bvh_device": (C.c_int32, [_P, C.c_uint64, C.c_int32, _P, C.POINTER(C.c_uint64), _P, C.POINTER(C.c_float)]),
     "rf_pt_create": (C.c_int32, [C.POINTER(_P)]),
     "rf_pt_destroy": (None, [_P]),
     "rf_pt_load": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),

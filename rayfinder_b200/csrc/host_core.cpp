@@ -1,6 +1,7 @@
 // Host-side pieces of the render path that the reference keeps on the CPU: error reporting,
 // createCamera, the Hosek-Wilkie sky state, the sampling lookup tables and the binned-SAH BVH
 // builder.  No GPU code here; compiled with -ffp-contract=off (strict fp32, see rf_vec.h).
+#include "bvh_common.h"
 #include "rf_internal.h"
 
 #include <algorithm>
@@ -263,29 +264,6 @@ extern "C" rf_status rf_sky_state_new(const rf_sky* sky, rf_sky_state* out)
 // ---------------------------------------------------------------------------------------------
 namespace
 {
-struct Box
-{
-    V3 lo{std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
-    V3 hi{std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest()};
-};
-// Aabb(p1, p2) re-applies min/max (aabb.hpp:20-26); merge() goes through it (aabb.hpp:50-58).
-inline Box makeBox(V3 a, V3 b) { return Box{vmin(a, b), vmax(a, b)}; }
-inline Box grow(const Box& b, V3 p) { return makeBox(vmin(b.lo, p), vmax(b.hi, p)); }
-inline Box grow(const Box& a, const Box& b) { return makeBox(vmin(a.lo, b.lo), vmax(a.hi, b.hi)); }
-inline float area(const Box& b)
-{
-    const V3 d = b.hi - b.lo;
-    return 2.0f * (d.x * d.y + d.x * d.z + d.y * d.z); // aabb.hpp:60-64
-}
-inline int widestAxis(const Box& b)
-{
-    const V3 d = b.hi - b.lo; // aabb.hpp:33-48: ties fall through to z
-    if (d.x > d.y && d.x > d.z) return 0;
-    if (d.y > d.z) return 1;
-    return 2;
-}
-inline float axisOf(V3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
-
 struct Prim
 {
     Box           box;
@@ -300,18 +278,9 @@ struct Builder
     std::uint64_t     numNodes = 0;
     std::uint64_t*    triangleIndices = nullptr;
 
-    static constexpr std::size_t NUM_BUCKETS = 12; // bvh.cpp:142-145
-    static constexpr std::size_t MAX_LEAF = 255;
-    static constexpr float       TRAVERSAL_COST = 0.5f;
-    static constexpr float       INTERSECTION_COST = 1.0f;
+    static constexpr std::size_t NUM_BUCKETS = BVH_NUM_BUCKETS;
 
-    static std::size_t bucketOf(const Prim& p, int axis, float lo, float hi)
-    {
-        // size_t(numBuckets * (c - lo) / (hi - lo)), clamped (bvh.cpp:152-155).
-        std::size_t b = static_cast<std::size_t>(
-            static_cast<float>(NUM_BUCKETS) * (axisOf(p.centroid, axis) - lo) / (hi - lo));
-        return std::min(b, NUM_BUCKETS - 1);
-    }
+    static std::size_t bucketOf(const Prim& p, int axis, float lo, float hi) { return bvhBucketOf(axisOf(p.centroid, axis), lo, hi); }
 
     void writeLeaf(std::uint64_t nodeIdx, const Box& box, std::size_t begin, std::size_t end, std::uint64_t firstTri)
     {
@@ -372,43 +341,13 @@ struct Builder
                 bucketBox[b] = grow(bucketBox[b], prims[i].box);
             }
 
-            constexpr std::size_t NUM_SPLITS = NUM_BUCKETS - 1;
-            float                 cost[NUM_SPLITS] = {};
-            {
-                std::size_t below = 0;
-                Box         boxBelow;
-                for (std::size_t i = 0; i < NUM_SPLITS; ++i)
-                {
-                    below += bucketCount[i];
-                    boxBelow = grow(boxBelow, bucketBox[i]);
-                    cost[i] += INTERSECTION_COST * static_cast<float>(below) * area(boxBelow);
-                }
-                std::size_t above = 0;
-                Box         boxAbove;
-                for (std::size_t i = NUM_SPLITS; i > 0; --i)
-                {
-                    above += bucketCount[i];
-                    boxAbove = grow(boxAbove, bucketBox[i]);
-                    cost[i - 1] += INTERSECTION_COST * static_cast<float>(above) * area(boxAbove);
-                }
-            }
-            float       minCost = std::numeric_limits<float>::max();
-            std::size_t splitBucket = static_cast<std::size_t>(-1);
-            for (std::size_t i = 0; i < NUM_SPLITS; ++i)
-            {
-                if (cost[i] < minCost)
-                {
-                    minCost = cost[i];
-                    splitBucket = i;
-                }
-            }
-            const float leafCost = INTERSECTION_COST * static_cast<float>(count);
-            const float totalCost = TRAVERSAL_COST + minCost / area(nodeBox);
-            if (!(count > MAX_LEAF || totalCost < leafCost))
+            const int chosen = bvhChooseSplit(bucketCount, bucketBox, nodeBox, count); // the SAH sweep, bvh.cpp:157-214
+            if (chosen < 0)
             {
                 writeLeaf(nodeIdx, nodeBox, begin, end, firstTri);
                 return nodeIdx;
             }
+            const std::size_t splitBucket = static_cast<std::size_t>(chosen);
             const auto mid = std::partition(first, last, [=](const Prim& p) {
                 return bucketOf(p, axis, cLo, cHi) <= splitBucket;
             });

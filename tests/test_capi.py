@@ -68,6 +68,9 @@ def test_no_cpu_fallback_without_a_device(duck_pt):
     with pytest.raises(rf.RayfinderError) as e:
         rf.ReferencePathTracer(params, (64, 64), rf.SceneArrays.from_pt(duck_pt))
     assert e.value.status == capi.RF_ERROR_CUDA
+    with pytest.raises(rf.RayfinderError) as e:
+        rf.build_bvh_device(O.triangles9(duck_pt)[:100])
+    assert e.value.status == capi.RF_ERROR_CUDA and "no CPU fallback" in str(e.value)
 
 
 def test_renderer_argument_validation(duck_pt):
