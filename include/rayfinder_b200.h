@@ -305,6 +305,22 @@ rf_status rf_bvh_visualizer_node_counts(
     uint32_t*           out_nodes_visited,
     float*              device_ms);
 
+/* Click-to-focus (pt/main.cpp:198-226): the camera ray through the cursor (u = x / width, v = 1 - y / height,
+ * generateCameraRay), rayIntersectBvh with rayTMax 1000, and on a hit focusDistance = dot(hit.p - camera_position,
+ * camera_forward).  A cursor outside the window or a miss leaves *out_focus_distance untouched and *out_hit 0, as
+ * the reference leaves its controller untouched. */
+rf_status rf_pick_focus_distance(
+    rf_traversal_scene* s,
+    const rf_camera*    camera,
+    const float         camera_position[3],
+    const float         camera_forward[3],
+    double              cursor_x,
+    double              cursor_y,
+    int32_t             window_width,
+    int32_t             window_height,
+    uint8_t*            out_hit,
+    float*              out_focus_distance);
+
 /* ---- host-side pieces the path keeps (no GPU needed) ------------------------------------------- */
 
 /* createCamera (common/camera.cpp:7-42). vfov in radians (Angle::asRadians). */

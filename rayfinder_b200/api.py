@@ -407,6 +407,16 @@ class TraversalScene:
         check(lib().rf_ray_intersect_bvh(self._handle, _ptr(rays), n, ray_t_max, _ptr(hit), _ptr(p_t), _ptr(nodes)))
         return hit.astype(bool), p_t, nodes
 
+    def pick_focus_distance(self, camera: capi.Camera, position, forward, cursor_x: float, cursor_y: float, window_width: int,
+                            window_height: int):
+        """Click-to-focus (pt/main.cpp:198-226): the new focus distance, or None for a miss / a cursor outside the window."""
+        pos = (C.c_float * 3)(*[float(x) for x in position])
+        fwd = (C.c_float * 3)(*[float(x) for x in forward])
+        hit, dist = C.c_uint8(0), C.c_float(0.0)
+        check(lib().rf_pick_focus_distance(self._handle, C.byref(camera), C.byref(pos), C.byref(fwd), cursor_x, cursor_y, window_width,
+                                           window_height, C.byref(hit), C.byref(dist)))
+        return dist.value if hit.value else None
+
     def bvh_visualizer_node_counts(self, camera: capi.Camera, width: int, height: int, ray_t_max: float = FLT_MAX):
         out = np.zeros((height, width), dtype=np.uint32)
         ms = C.c_float()

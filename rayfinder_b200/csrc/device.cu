@@ -1001,6 +1001,38 @@ extern "C" rf_status rf_ray_intersect_bvh(
     return RF_OK;
 }
 
+// Click-to-focus, pt/main.cpp:198-226: the ray through the cursor, rayIntersectBvh(ray, bvhNodes, positions, 1000.f,
+// hitData), focusDistance = dot(hitData.p - cameraPosition, cameraForward).
+extern "C" rf_status rf_pick_focus_distance(
+    rf_traversal_scene* s,
+    const rf_camera*    camera,
+    const float         cameraPosition[3],
+    const float         cameraForward[3],
+    const double        cursorX,
+    const double        cursorY,
+    const std::int32_t  windowWidth,
+    const std::int32_t  windowHeight,
+    std::uint8_t*       outHit,
+    float*              outFocusDistance)
+{
+    if (!s || !camera || !cameraPosition || !cameraForward || !outHit || !outFocusDistance || windowWidth <= 0 || windowHeight <= 0)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pick_focus_distance: bad argument");
+    *outHit = 0;
+    // main.cpp:207-208: clicks outside the window are ignored
+    if (!(cursorX >= 0.0 && cursorX < static_cast<double>(windowWidth) && cursorY >= 0.0 && cursorY < static_cast<double>(windowHeight))) return RF_OK;
+    const float u = static_cast<float>(cursorX) / static_cast<float>(windowWidth);
+    const float v = 1.f - static_cast<float>(cursorY) / static_cast<float>(windowHeight);
+    // generateCameraRay, camera.cpp:44-51
+    const V3    origin = v3(camera->origin);
+    const V3    dir = normalize(((v3(camera->lower_left_corner) + v3(camera->horizontal) * u) + v3(camera->vertical) * v) - origin);
+    const float ray[6] = {origin.x, origin.y, origin.z, dir.x, dir.y, dir.z};
+    float       pt[4] = {};
+    const rf_status st = rf_ray_intersect_bvh(s, ray, 1, 1000.f, outHit, pt, nullptr);
+    if (st != RF_OK) return st;
+    if (*outHit) *outFocusDistance = dot(v3(pt) - v3(cameraPosition), v3(cameraForward));
+    return RF_OK;
+}
+
 extern "C" rf_status rf_bvh_visualizer_node_counts(
     rf_traversal_scene* s,
     const rf_camera*    camera,

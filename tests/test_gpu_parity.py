@@ -357,3 +357,35 @@ def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames):
     for key in O.COUNTER_NAMES:
         assert stats[key] == ref_stats[key], key
     assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
+
+
+def test_click_to_focus_matches_reference_formula(duck_pt):
+    """pt/main.cpp:198-226: ray through the cursor, rayIntersectBvh(..., 1000.f, ...), dot(hit.p - position, forward)."""
+    f32 = np.float32
+    tris = O.triangles9(duck_pt)
+    scene = rf.TraversalScene(duck_pt.bvh_nodes, tris)
+    w, h = 640, 480
+    cam = rf.bvh_visualizer_camera(duck_pt.bvh_nodes, w, h)
+    c = rf.camera_to_array(cam)
+    origin, lower_left, horizontal, vertical = c[0:3], c[3:6], c[6:9], c[9:12]
+    forward = np.cross(c[12:15], c[15:18]).astype(f32)  # up x right (camera.cpp: up = cross(right, forward))
+    forward /= np.linalg.norm(forward)
+    hits = 0
+    for x, y in [(320.0, 240.0), (100.5, 50.25), (639.9, 479.9), (0.0, 0.0), (333.0, 300.0), (-1.0, 5.0), (640.0, 10.0), (300.25, 220.0),
+                 (345.5, 255.0), (310.0, 262.75), (290.0, 240.0), (330.0, 215.5)]:
+        got = scene.pick_focus_distance(cam, origin, forward, x, y, w, h)
+        if not (0.0 <= x < w and 0.0 <= y < h):
+            assert got is None
+            continue
+        u, v = f32(x) / f32(w), f32(1.0) - f32(y) / f32(h)
+        d = ((lower_left + horizontal * u) + vertical * v) - origin
+        d = d * (f32(1.0) / np.sqrt(f32(f32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])))
+        hit, p_t, _ = O.oracle_intersect(duck_pt.bvh_nodes, tris, np.concatenate([origin, d])[None, :].astype(f32), 1000.0)
+        if not hit[0]:
+            assert got is None
+            continue
+        hits += 1
+        rel = p_t[0, :3] - origin
+        expected = f32(f32(rel[0] * forward[0] + rel[1] * forward[1]) + rel[2] * forward[2])
+        assert f32(got) == expected
+    assert hits >= 3
