@@ -265,6 +265,35 @@ rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t p
  * GPU owns at most ~0.6 M pixels — launches that are mostly tail — else off), up to 32. */
 rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
 
+/* ---- the deferred renderer's lighting + resolve passes as a second integrator -------
+ * pt/deferred_renderer_lighting_pass.wgsl:96-186 and pt/deferred_renderer_resolve_pass.wgsl:34-53, i.e. the
+ * `lightingPass` and `resolvePass` of DeferredRenderer::render (pt/deferred_renderer.cpp:340-375).  The G-buffer
+ * the reference's rasteriser produces is an input here. */
+typedef struct rf_deferred_lighting_params
+{
+    float    inverse_view_reverse_z_projection[16]; /* Uniforms.inverseViewReverseZProjectionMat, column-major */
+    float    camera_eye[4];                          /* Uniforms.cameraEye */
+    uint32_t framebuffer_width;                      /* Uniforms.framebufferSize */
+    uint32_t framebuffer_height;
+    uint32_t frame_count;                            /* Uniforms.frameCount (0 restarts the moving average) */
+    float    exposure;                               /* resolve pass Uniforms.exposure */
+    rf_sky   sky;                                    /* -> SkyState, as for the path tracer */
+} rf_deferred_lighting_params;
+
+/* One frame of the lighting pass (sun sample at the G-buffer surface, one bounce, sun sample or sky there) followed by the
+ * resolve pass's moving average.  G-buffer, host memory, row-major, row 0 = top, what textureLoad returns per texel:
+ * albedo and normal 4 floats (rgb + unused; the normal ENCODED as 0.5 n + 0.5), depth 1 float (reverse Z: 0 = no
+ * surface).  The framebuffer size must not exceed the renderer's maxFramebufferSize; the scene is the renderer's. */
+rf_status rf_renderer_render_deferred_lighting(
+    rf_renderer*                       r,
+    const rf_deferred_lighting_params* params,
+    const float*                       gbuffer_albedo,
+    const float*                       gbuffer_normal,
+    const float*                       gbuffer_depth);
+/* sampleBuffer and accumulationBuffer (3 floats per pixel) and the resolve pass's BGRA8 output of the last deferred
+ * frame; each pointer may be NULL. */
+rf_status rf_renderer_read_deferred(rf_renderer* r, float* sample_rgb, float* accumulation_rgb, uint32_t* display_bgra8);
+
 /* ---- the CPU traversal twin: nlrs::rayIntersectBvh (common/ray_intersection.hpp:43-49) --------- */
 
 typedef struct rf_traversal_scene rf_traversal_scene;

@@ -83,11 +83,13 @@ constexpr float FRAC_1_PI = 0.31830987f;
 constexpr float T_MAX = 10000.0f; // wgsl:73
 
 // ---- offsetRay: ray_intersection.cpp:17-35 / wgsl:523-544 ---------------------------------------
-vec3 offsetRay(vec3 p, vec3 n)
+// The deferred renderer's offsetPosition (deferred_renderer_lighting_pass.wgsl:497-519) is the same function with
+// FLOAT_SCALE 1/16384 and INT_SCALE 1024; `deferred` selects it.
+vec3 offsetRay(vec3 p, vec3 n, bool deferred = false)
 {
     const float ORIGIN = 1.0f / 32.0f;
-    const float FLOAT_SCALE = 1.0f / 65536.0f;
-    const float INT_SCALE = 256.0f;
+    const float FLOAT_SCALE = deferred ? 1.0f / 16384.0f : 1.0f / 65536.0f;
+    const float INT_SCALE = deferred ? 1024.0f : 256.0f;
     const int   ox = int(INT_SCALE * n.x), oy = int(INT_SCALE * n.y), oz = int(INT_SCALE * n.z);
     const vec3  po = {
         std::bit_cast<float>(std::bit_cast<int>(p.x) + (p.x < 0 ? -ox : ox)),
@@ -106,7 +108,7 @@ struct TriangleHit
     vec3  b;
     float t;
 };
-bool rayIntersectTriangle(const Ray& ray, vec3 p0, vec3 p1, vec3 p2, float tmax, TriangleHit& hit)
+bool rayIntersectTriangle(const Ray& ray, vec3 p0, vec3 p1, vec3 p2, float tmax, TriangleHit& hit, bool deferred = false)
 {
     const vec3  e1 = p1 - p0;
     const vec3  e2 = p2 - p0;
@@ -125,7 +127,7 @@ bool rayIntersectTriangle(const Ray& ray, vec3 p0, vec3 p1, vec3 p2, float tmax,
     {
         const vec3 p = p0 + u * e1 + v * e2;
         const vec3 n = normalize(cross(e1, e2));
-        hit.p = offsetRay(p, n);
+        hit.p = offsetRay(p, n, deferred);
         hit.b = {1.0f - u - v, u, v};
         hit.t = t;
         return true;
@@ -185,6 +187,7 @@ struct SceneView
     std::uint64_t           numTexels;
     const float*            blueNoise; // vec2f per texel = u8 / 255 (reference_path_tracer.cpp:174-177)
     std::uint32_t           bnWidth, bnHeight;
+    bool                    deferred = false; // the deferred renderer's lighting pass: its offsetPosition constants
 };
 
 struct Intersection // wgsl:158-163
@@ -226,7 +229,7 @@ bool rayIntersectBvh(
                     const float*        t = scene.tris + static_cast<std::size_t>(triangleIdx) * 3 * scene.triStride;
                     TriangleHit         trihit;
                     ++trisTested;
-                    if (rayIntersectTriangle(ray, load3(t), load3(t + scene.triStride), load3(t + 2 * scene.triStride), tmax, trihit))
+                    if (rayIntersectTriangle(ray, load3(t), load3(t + scene.triStride), load3(t + 2 * scene.triStride), tmax, trihit, scene.deferred))
                     {
                         tmax = trihit.t;
                         didIntersect = true;
@@ -710,6 +713,154 @@ double oracle_render_frame(const OracleScene* sc, const OracleFrame* fr, float* 
         }
     }
     return seconds;
+}
+
+// ---- the deferred renderer's lighting pass: pt/deferred_renderer_lighting_pass.wgsl ------------------------------
+struct OracleDeferred
+{
+    float         inverseViewReverseZProjection[16]; // column-major
+    float         cameraEye[4];
+    std::uint32_t width, height, frameCount;
+    float         skyState[40];
+};
+
+// skyRadiance of the lighting pass (:203-236): the path tracer's plus the solar disk.
+static float deferredSkyRadiance(const SkyState& sky, float theta, float gamma, std::uint32_t channel)
+{
+    const float terrestrialSolarRadius = 0.255f * (PI / 180.0f);
+    const float solarDiskRadius = gamma / terrestrialSolarRadius;
+    const float solarRadiance = solarDiskRadius <= 1.0f ? sky.solarRadiances[channel] : 0.0f;
+    return skyRadiance(sky, theta, gamma, channel) + solarRadiance;
+}
+static vec3 deferredSky(const SkyState& sky, vec3 v)
+{
+    const float theta = std::acos(v.y);
+    float       c = dot(v, load3(sky.sunDirection));
+    c = stdMin(stdMax(c, -1.0f), 1.0f);
+    const float gamma = std::acos(c);
+    return {deferredSkyRadiance(sky, theta, gamma, 0u), deferredSkyRadiance(sky, theta, gamma, 1u), deferredSkyRadiance(sky, theta, gamma, 2u)};
+}
+// worldFromUv (:132-138); mat4x4 * vec4 as ((c0 x + c1 y) + c2 z) + c3 w.
+static vec3 worldFromUv(const OracleDeferred& un, float uvx, float uvy, float depth)
+{
+    const float  nx = 2.0f * uvx - 1.0f, ny = 2.0f * (1.0f - uvy) - 1.0f;
+    const float* m = un.inverseViewReverseZProjection;
+    float        w4[4];
+    for (int r = 0; r < 4; ++r) w4[r] = ((m[0 + r] * nx + m[4 + r] * ny) + m[8 + r] * depth) + m[12 + r] * 1.0f;
+    return {w4[0] / w4[3], w4[1] / w4[3], w4[2] / w4[3]};
+}
+// lightSample (:188-200)
+static vec3 deferredLightSample(const SceneView& scene, const SkyState& sky, const float u[2], vec3 position, vec3 normal, vec3 albedo, Counters& ctr)
+{
+    const Constants k = constants();
+    const vec3      lightDirection = mul(pixarOnb(load3(sky.sunDirection)), directionInCone(u, k.solarCosThetaMax));
+    const vec3      lightIntensity = {sky.solarRadiances[0], sky.solarRadiances[1], sky.solarRadiances[2]};
+    const vec3      brdf = albedo * FRAC_1_PI;
+    const vec3      reflectance = brdf * dot(normal, lightDirection);
+    ++ctr.shadowRays;
+    const float lightVisibility = shadowRay(scene, Ray{position, lightDirection}, T_MAX, ctr.shadowNodes, ctr.shadowTris);
+    return lightIntensity * reflectance * lightVisibility * k.solarInvPdf;
+}
+
+// main + surfaceColor (:96-186) for every pixel.  G-buffer: albedo / encoded normal 4 floats per texel, depth 1 float
+// (reverse Z).  sample: 3 floats per pixel (sampleBuffer).  counters9 as oracle_render_frame ("paths" = surface pixels).
+double oracle_deferred_lighting(
+    const OracleScene* sc, const OracleDeferred* un, const float* albedo4, const float* normal4, const float* depth, float* sample, std::uint64_t* counters9,
+    int numThreads)
+{
+    std::vector<float> bn(128 * 128 * 2);
+    for (std::size_t i = 0; i < bn.size(); ++i) bn[i] = static_cast<float>(sc->blueNoiseRg8[i]) / 255.0f;
+    SceneView scene{};
+    scene.nodes = static_cast<const BvhNode*>(sc->nodes);
+    scene.tris = sc->positionAttributes;
+    scene.triStride = 4;
+    scene.vattr = static_cast<const VertexAttributes*>(sc->vertexAttributes);
+    scene.texDesc = sc->texDesc;
+    scene.numTextures = sc->numTextures;
+    scene.texels = sc->texels;
+    scene.numTexels = sc->numTexels;
+    scene.blueNoise = bn.data();
+    scene.bnWidth = 128, scene.bnHeight = 128;
+    scene.deferred = true;
+    SkyState sky;
+    std::memcpy(&sky, un->skyState, sizeof(SkyState));
+    const std::uint32_t W = un->width, H = un->height;
+    if (numThreads < 1) numThreads = 1;
+    std::vector<Counters> perThread(numThreads);
+    const auto            t0 = std::chrono::steady_clock::now();
+    parallelRows(0, static_cast<int>(H), numThreads, [&](int py, int tid) {
+        Counters& ctr = perThread[tid];
+        for (std::uint32_t px = 0; px < W; ++px)
+        {
+            const std::size_t texel = static_cast<std::size_t>(py) * W + px;
+            const float       uvx = (static_cast<float>(px) + 0.5f) / static_cast<float>(W);
+            const float       uvy = (static_cast<float>(py) + 0.5f) / static_cast<float>(H);
+            const float       depthSample = depth[texel];
+            vec3              color = {0.f, 0.f, 0.f};
+            if (depthSample == 0.0f)
+            {
+                const vec3 world = worldFromUv(*un, uvx, uvy, depthSample);
+                color = deferredSky(sky, normalize(world - load3(un->cameraEye)));
+            }
+            else
+            {
+                const std::uint32_t cx = static_cast<std::uint32_t>(uvx * static_cast<float>(W));
+                const std::uint32_t cy = static_cast<std::uint32_t>(uvy * static_cast<float>(H));
+                vec3                position = worldFromUv(*un, uvx, uvy, depthSample);
+                const float*        en = normal4 + 4 * texel;
+                vec3                normal = {2.0f * en[0] - 1.0f, 2.0f * en[1] - 1.0f, 2.0f * en[2] - 1.0f};
+                vec3                alb = load3(albedo4 + 4 * texel);
+                position = offsetRay(position, normal, true);
+                ++ctr.paths;
+                // surfaceColor (:142-186), NUM_BOUNCES = 2
+                vec3  radiance = {0.f, 0.f, 0.f};
+                vec3  throughput = {1.f, 1.f, 1.f};
+                float blueNoise[2];
+                animatedBlueNoise(scene, cx, cy, un->frameCount, 1u << 20, blueNoise);
+                radiance = radiance + throughput * deferredLightSample(scene, sky, blueNoise, position, normal, alb, ctr);
+                for (int bounce = 1; bounce < 2; ++bounce)
+                {
+                    const vec3 wi = mul(pixarOnb(normal), directionInCosineWeightedHemisphere(blueNoise));
+                    const Ray  ray{position, wi};
+                    throughput = throughput * alb;
+                    Intersection hit;
+                    ++ctr.closestRays;
+                    if (rayIntersectBvh(scene, ray, T_MAX, &hit, nullptr, nullptr, ctr.closestNodes, ctr.closestTris))
+                    {
+                        position = hit.p;
+                        normal = hit.n;
+                        alb = textureLookup(scene, hit.textureDescriptorIdx, hit.uv);
+                    }
+                    else
+                    {
+                        radiance = radiance + throughput * deferredSky(sky, ray.direction);
+                        break;
+                    }
+                    radiance = radiance + throughput * deferredLightSample(scene, sky, blueNoise, position, normal, alb, ctr);
+                }
+                color = radiance;
+            }
+            sample[3 * texel] = color.x, sample[3 * texel + 1] = color.y, sample[3 * texel + 2] = color.z;
+        }
+    });
+    const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (counters9)
+    {
+        for (const Counters& c : perThread)
+        {
+            counters9[0] += c.paths, counters9[1] += c.closestRays, counters9[2] += c.shadowRays, counters9[3] += c.closestNodes;
+            counters9[4] += c.closestTris, counters9[5] += c.shadowNodes, counters9[6] += c.shadowTris;
+        }
+    }
+    return seconds;
+}
+
+// resolve pass, pt/deferred_renderer_resolve_pass.wgsl:34-50 (the moving average; the tone mapping is oracle_display with
+// accumulatedSampleCount 1 on a 4-float copy).
+void oracle_deferred_resolve(const float* sample, float* accumulation, std::uint64_t numPixels, std::uint32_t frameCount)
+{
+    for (std::uint64_t i = 0; i < 3 * numPixels; ++i)
+        accumulation[i] = frameCount == 0u ? sample[i] : 0.1f * sample[i] + 0.9f * accumulation[i];
 }
 
 // fsMain:59-63 + acesFilmic:278-285, packed as BGRA8 unorm (the reference's swap-chain format).

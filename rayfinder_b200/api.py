@@ -336,6 +336,32 @@ class ReferencePathTracer:
         check(lib().rf_renderer_read_display(self._handle, _ptr(out), out.size))
         return out
 
+    def render_deferred_lighting(self, inverse_view_projection: np.ndarray, camera_eye, frame_count: int, albedo: np.ndarray,
+                                 normal: np.ndarray, depth: np.ndarray, sky: "Sky | None" = None, exposure: float = 1.0) -> None:
+        """One frame of the deferred renderer's lighting + resolve passes (csrc/deferred.cuh).  ``inverse_view_projection``:
+        (4, 4) with ``m[c]`` = column c (glm / WGSL order); G-buffer: albedo / encoded normal (h, w, 4) float32, reverse-Z
+        depth (h, w) float32 (0 = sky)."""
+        h, w = depth.shape
+        p = capi.DeferredLightingParams()
+        p.inverse_view_reverse_z_projection[:] = [float(x) for x in np.asarray(inverse_view_projection, dtype=np.float32).reshape(16)]
+        p.camera_eye[:] = [float(camera_eye[0]), float(camera_eye[1]), float(camera_eye[2]), 1.0]
+        p.framebuffer_width, p.framebuffer_height, p.frame_count, p.exposure = w, h, frame_count, exposure
+        p.sky = (sky or Sky()).to_c()
+        a = np.ascontiguousarray(albedo, dtype=np.float32).reshape(h, w, 4)
+        n = np.ascontiguousarray(normal, dtype=np.float32).reshape(h, w, 4)
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        check(lib().rf_renderer_render_deferred_lighting(self._handle, C.byref(p), _ptr(a), _ptr(n), _ptr(d)))
+        self._deferred_size = (w, h)
+
+    def read_deferred(self):
+        """(sampleBuffer (h, w, 3), accumulationBuffer (h, w, 3), BGRA8 display (h, w)) of the last deferred frame."""
+        w, h = self._deferred_size
+        sample = np.empty((h, w, 3), dtype=np.float32)
+        accumulation = np.empty((h, w, 3), dtype=np.float32)
+        display = np.empty((h, w), dtype=np.uint32)
+        check(lib().rf_renderer_read_deferred(self._handle, _ptr(sample), _ptr(accumulation), _ptr(display)))
+        return sample, accumulation, display
+
     def hdr_device_ptr(self) -> int:
         return lib().rf_renderer_hdr_device_ptr(self._handle) or 0
 

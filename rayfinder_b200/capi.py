@@ -66,6 +66,12 @@ class RenderParameters(C.Structure):  # pt/reference_path_tracer.hpp:34-43
                 ("sampling_params", SamplingParams), ("sky", Sky), ("exposure", C.c_float)]
 
 
+class DeferredLightingParams(C.Structure):  # deferred_renderer_lighting_pass.wgsl:8-13 + resolve pass Uniforms
+    _fields_ = [("inverse_view_reverse_z_projection", C.c_float * 16), ("camera_eye", C.c_float * 4),
+                ("framebuffer_width", C.c_uint32), ("framebuffer_height", C.c_uint32), ("frame_count", C.c_uint32),
+                ("exposure", C.c_float), ("sky", Sky)]
+
+
 class RendererDescriptor(C.Structure):  # pt/reference_path_tracer.hpp:53-57
     _fields_ = [("render_params", RenderParameters), ("max_framebuffer_width", C.c_int32),
                 ("max_framebuffer_height", C.c_int32)]
@@ -110,6 +116,8 @@ SIGNATURES = {
     "rf_renderer_set_tuning": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rf_renderer_set_pipeline": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "rf_renderer_set_tail_policy": (C.c_int32, [_P, C.c_int32]),
+    "rf_renderer_render_deferred_lighting": (C.c_int32, [_P, C.POINTER(DeferredLightingParams), _P, _P, _P]),
+    "rf_renderer_read_deferred": (C.c_int32, [_P, _P, _P, _P]),
     "rf_traversal_scene_create": (C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(_P)]),
     "rf_traversal_scene_destroy": (None, [_P]),
     "rf_ray_intersect_bvh": (C.c_int32, [_P, _P, C.c_uint64, C.c_float, _P, _P, _P]),

@@ -4,6 +4,7 @@
 //
 // Compiled by nvcc for sm_100a only, with -fmad=false (see rf_vec.h).  There is no CPU fallback:
 // every entry point fails with RF_ERROR_CUDA when no device is usable.
+#include "deferred.cuh"
 #include "mega.cuh"
 
 #include <algorithm>
@@ -261,6 +262,19 @@ struct rf_renderer
     };
     static constexpr int MAX_SUBFRAMES = 4;
     SubFrame    sub[MAX_SUBFRAMES];
+    // The deferred renderer's lighting pass (deferred.cuh): G-buffer copies, its own queues and EMA buffer; allocated
+    // by the first rf_renderer_render_deferred_lighting call.
+    struct Deferred
+    {
+        DeviceBuffer<float4>        albedo, normal, queueMem, accumulation;
+        DeviceBuffer<float>         depth;
+        DeviceBuffer<HitRecord>     hits;
+        DeviceBuffer<std::uint32_t> counters;
+        DeviceBuffer<SampleLutRow>  lutRow;
+        std::uint64_t               capacity = 0;
+        std::uint32_t               width = 0, height = 0;
+        float                       exposure = 1.0f;
+    } deferred;
     std::uint64_t kernelLaunches = 0;   // kernels launched by render() since the last reset_stats
     int         numSubFrames = 2;       // in effect (updateTiles)
     int         requestedSubFrames = 0; // 0: automatic
@@ -734,6 +748,126 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     r->frames++;
     r->accumulated = std::min(r->accumulated + 1, spp); // reference_path_tracer.cpp:590-591
 
+    return RF_OK;
+}
+
+// DeferredRenderer::render's lighting pass + resolve pass (pt/deferred_renderer.cpp:340-375) on a caller-supplied
+// G-buffer; see deferred.cuh.
+extern "C" rf_status rf_renderer_render_deferred_lighting(
+    rf_renderer*                       r,
+    const rf_deferred_lighting_params* p,
+    const float*                       gbufferAlbedo,
+    const float*                       gbufferNormal,
+    const float*                       gbufferDepth)
+{
+    if (!r || !p || !gbufferAlbedo || !gbufferNormal || !gbufferDepth)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_render_deferred_lighting: null argument");
+    if (p->framebuffer_width == 0 || p->framebuffer_height == 0 || p->framebuffer_width > r->maxW || p->framebuffer_height > r->maxH)
+        return setError(RF_ERROR_INVALID_ARGUMENT, "Framebuffer size %ux%u outside (0, %ux%u].", p->framebuffer_width, p->framebuffer_height, r->maxW, r->maxH);
+    RF_CUDA(cudaSetDevice(r->device));
+    rf_sky_state    sky{};
+    const rf_status st = rf_sky_state_new(&p->sky, &sky);
+    if (st != RF_OK) return st;
+
+    rf_renderer::Deferred& d = r->deferred;
+    const std::uint32_t    w = p->framebuffer_width, h = p->framebuffer_height;
+    const std::uint64_t    numPixels = static_cast<std::uint64_t>(w) * h;
+    cudaStream_t           s = r->stream;
+    if (numPixels > d.capacity)
+    {
+        RF_CUDA(cudaStreamSynchronize(s));
+        RF_CUDA(d.albedo.allocate(numPixels));
+        RF_CUDA(d.normal.allocate(numPixels));
+        RF_CUDA(d.depth.allocate(numPixels));
+        RF_CUDA(d.accumulation.allocate(numPixels));
+        RF_CUDA(d.queueMem.allocate(numPixels * 8));
+        RF_CUDA(d.hits.allocate(numPixels));
+        if (!d.counters.ptr) RF_CUDA(d.counters.allocate(counterSlots(1)));
+        if (!d.lutRow.ptr) RF_CUDA(d.lutRow.allocate(1));
+        d.capacity = numPixels;
+    }
+    if (w != d.width || h != d.height) RF_CUDA(cudaMemsetAsync(d.accumulation.ptr, 0, numPixels * sizeof(float4), s));
+    d.width = w, d.height = h, d.exposure = p->exposure;
+    PathQueue queues[2];
+    for (int q = 0; q < 2; ++q)
+    {
+        float4* base = d.queueMem.ptr + static_cast<std::uint64_t>(q) * 4 * numPixels;
+        queues[q] = PathQueue{base, base + numPixels, base + 2 * numPixels, base + 3 * numPixels};
+    }
+
+    // host -> device: the G-buffer of this frame and the sampling table of animatedBlueNoise(coord, frameCount, 1 << 20)
+    RF_CUDA(cudaMemcpyAsync(d.albedo.ptr, gbufferAlbedo, numPixels * sizeof(float4), cudaMemcpyHostToDevice, s));
+    RF_CUDA(cudaMemcpyAsync(d.normal.ptr, gbufferNormal, numPixels * sizeof(float4), cudaMemcpyHostToDevice, s));
+    RF_CUDA(cudaMemcpyAsync(d.depth.ptr, gbufferDepth, numPixels * sizeof(float), cudaMemcpyHostToDevice, s));
+    SampleLutRow row;
+    buildSampleLutRow(p->frame_count % (1u << 20), row);
+    RF_CUDA(cudaMemcpyAsync(d.lutRow.ptr, &row, sizeof(row), cudaMemcpyHostToDevice, s));
+    RF_CUDA(cudaStreamSynchronize(s)); // `row` and the caller's buffers may go away
+
+    FrameParams fp{};
+    fp.width = w, fp.height = h;
+    fp.frameCount = p->frame_count;
+    fp.sampleIndex = 0; // the one row of d.lutRow
+    fp.numBounces = 1;  // NUM_BOUNCES = 2 counts the G-buffer surface
+    fp.numTextures = r->numTextures;
+    fp.numTexels = r->numTexels;
+    fp.sky = sky;
+    const SolarConstants sc = solarConstants();
+    fp.solarCosThetaMax = sc.cosThetaMax;
+    fp.solarInvPdf = sc.invPdf;
+    fp.deferred = 1u;
+    SceneDevice scene{r->nodes.ptr, r->tris.ptr, r->vattr.ptr, r->texDesc.ptr, r->texels.ptr, r->blueNoise.ptr, d.lutRow.ptr, r->srgbLut.ptr,
+                      r->ordered, r->tuning};
+    DeferredUniforms un{};
+    std::memcpy(un.inverseViewReverseZProjection, p->inverse_view_reverse_z_projection, sizeof(un.inverseViewReverseZProjection));
+    std::memcpy(un.cameraEye, p->camera_eye, sizeof(un.cameraEye));
+    un.frameCount = p->frame_count;
+
+    std::uint32_t* ctr = d.counters.ptr;
+    std::uint32_t* const cursors = ctr + 2;
+    const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u};
+    const int gridLight = r->gridFor(8);
+    const int gridTrace = r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
+    RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(1) * sizeof(std::uint32_t), s));
+    k_deferred_primary<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, un, d.albedo.ptr, d.normal.ptr, d.depth.ptr, queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
+    // shadow rays of the G-buffer surfaces + the bounce rays
+    launchTrace(r->variant, r->traceBlock, gridTrace, s, fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[0], &ctr[0], r->radiance.ptr, &cursors[0], noHandOver, r->stats.ptr);
+    k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr);
+    // shadow rays of the bounce hits
+    launchTrace(r->variant, r->traceBlock, gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], noHandOver, r->stats.ptr);
+    k_deferred_resolve<<<gridLight, BLOCK_THREADS, 0, s>>>(static_cast<std::uint32_t>(numPixels), p->frame_count, r->radiance.ptr, d.accumulation.ptr);
+    RF_CUDA(cudaGetLastError());
+    r->kernelLaunches += 5;
+    r->frames++;
+    return RF_OK;
+}
+
+// sampleBuffer / accumulationBuffer (array<array<f32, 3>>, deferred_renderer_lighting_pass.wgsl:87, resolve pass :31-32) and
+// the resolve pass's colour attachment (aces(exposure * colour)^(1/2.2), BGRA8) of the last deferred frame.  Each may be NULL.
+extern "C" rf_status rf_renderer_read_deferred(rf_renderer* r, float* sampleRgb, float* accumulationRgb, std::uint32_t* displayBgra8)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_deferred: null renderer");
+    rf_renderer::Deferred& d = r->deferred;
+    if (d.width == 0) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_deferred: no deferred frame rendered yet");
+    RF_CUDA(cudaSetDevice(r->device));
+    const std::uint64_t numPixels = static_cast<std::uint64_t>(d.width) * d.height;
+    std::vector<float4> tmp(numPixels);
+    const auto          fetch = [&](const float4* src, float* dst) -> cudaError_t {
+        const cudaError_t err = cudaMemcpyAsync(tmp.data(), src, numPixels * sizeof(float4), cudaMemcpyDeviceToHost, r->stream);
+        if (err != cudaSuccess) return err;
+        const cudaError_t err2 = cudaStreamSynchronize(r->stream);
+        for (std::uint64_t i = 0; i < numPixels && err2 == cudaSuccess; ++i) dst[3 * i] = tmp[i].x, dst[3 * i + 1] = tmp[i].y, dst[3 * i + 2] = tmp[i].z;
+        return err2;
+    };
+    if (sampleRgb) RF_CUDA(fetch(r->radiance.ptr, sampleRgb));
+    if (accumulationRgb) RF_CUDA(fetch(d.accumulation.ptr, accumulationRgb));
+    if (displayBgra8)
+    {
+        k_display<<<r->gridFor(8), BLOCK_THREADS, 0, r->stream>>>(static_cast<std::uint32_t>(numPixels), d.accumulation.ptr, 1.0f, d.exposure, r->display.ptr);
+        RF_CUDA(cudaGetLastError());
+        RF_CUDA(cudaMemcpyAsync(displayBgra8, r->display.ptr, numPixels * 4, cudaMemcpyDeviceToHost, r->stream));
+        RF_CUDA(cudaStreamSynchronize(r->stream));
+    }
     return RF_OK;
 }
 

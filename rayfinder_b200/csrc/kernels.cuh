@@ -45,6 +45,8 @@ struct FrameParams
     rf_sky_state  sky;
     float         solarCosThetaMax;
     float         solarInvPdf;
+    std::uint32_t deferred; // 1: the deferred renderer's lighting pass (deferred.cuh): its offsetPosition constants, the solar
+                            // disk in the sky, and `radiance += throughput * (lightIntensity * reflectance * vis * invPdf)`
 };
 
 struct SceneDevice
@@ -207,6 +209,12 @@ __device__ __forceinline__ float skyRadianceChannel(const rf_sky_state& sky, con
     const float  radianceRhs = p[2] + p[3] * expM + p[5] * rayM + p[6] * mieM + p[7] * zenith;
     return r * (radianceLhs * radianceRhs);
 }
+// The deferred renderer's skyRadiance adds the solar disk (deferred_renderer_lighting_pass.wgsl:229-235).
+__device__ __forceinline__ float solarDiskRadiance(const rf_sky_state& sky, const float gamma, const int ch)
+{
+    const float TERRESTRIAL_SOLAR_RADIUS = 0.255f * (3.1415927f / 180.0f);
+    return __fdiv_rn(gamma, TERRESTRIAL_SOLAR_RADIUS) <= 1.0f ? sky.solar_radiances[ch] : 0.0f;
+}
 
 // rayColor miss branch, wgsl:212-229: sky radiance along the (possibly unnormalised) direction v.
 __device__ __forceinline__ V3 skyForMiss(const FrameParams& fp, const V3 v, const V3 sunDir)
@@ -215,7 +223,9 @@ __device__ __forceinline__ V3 skyForMiss(const FrameParams& fp, const V3 v, cons
     float       cosSun = dot(v, sunDir);
     cosSun = fminf(fmaxf(cosSun, -1.0f), 1.0f);
     const float gamma = acosf(cosSun);
-    return v3(skyRadianceChannel(fp.sky, theta, gamma, 0), skyRadianceChannel(fp.sky, theta, gamma, 1), skyRadianceChannel(fp.sky, theta, gamma, 2));
+    V3          sky = v3(skyRadianceChannel(fp.sky, theta, gamma, 0), skyRadianceChannel(fp.sky, theta, gamma, 1), skyRadianceChannel(fp.sky, theta, gamma, 2));
+    if (fp.deferred) sky = sky + v3(solarDiskRadiance(fp.sky, gamma, 0), solarDiskRadiance(fp.sky, gamma, 1), solarDiskRadiance(fp.sky, gamma, 2));
+    return sky;
 }
 
 // rayColor hit branch, wgsl:191-211, for the final (closest) accepted triangle of a path at pixel `idx`:
@@ -230,7 +240,7 @@ __device__ __forceinline__ SurfaceShade shadeSurfaceHit(
 {
     SurfaceShade out;
     // Intersection of the final (closest) accepted triangle, wgsl:393-400.
-    out.p = hitPoint(scene.tris, hit);
+    out.p = hitPoint(scene.tris, hit, fp.deferred != 0u);
     const float  b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
     const float4 a0 = ldg4(scene.vattr + 5 * hit.tri + 0);
     const float4 a1 = ldg4(scene.vattr + 5 * hit.tri + 1);
@@ -271,6 +281,15 @@ __device__ __forceinline__ SurfaceShade shadeSurfaceHit(
     const V3    brdf = albedo * FRAC_1_PI;
     const V3    reflectance = brdf * dot(nrm, lightDir);
     out.contribution = (throughput * lightIntensity) * reflectance;
+    if (fp.deferred)
+    {
+        // lightSample (deferred_renderer_lighting_pass.wgsl:188-200) keeps the throughput outside: the traversal launch adds
+        // throughput * (lightIntensity * reflectance * visibility * SOLAR_INV_PDF); bounce 1 is the last one (NUM_BOUNCES = 2)
+        out.contribution = lightIntensity * reflectance;
+        out.wi = v3(0.f, 0.f, 0.f);
+        out.nextThroughput = throughput;
+        return out;
+    }
 
     // evalImplicitLambertian -> directionInCosineWeightedHemisphere, wgsl:295-301,583-592.
     const float hemiSin = __fsqrt_rn(1.0f - ux);
@@ -403,6 +422,17 @@ struct TraceIO : CursorSource
         const float         vis = didHit ? 0.0f : 1.0f; // "Returns 1.0 if no forward intersections, 0.0 otherwise"
         const float4        c = shadowQueue.contribution[j];
         float4              rad = radiance[idx];
+        if (fp.deferred)
+        {
+            // radiance += throughput * lightSample(...) (deferred_renderer_lighting_pass.wgsl:153,182); c.w != 0 marks the
+            // primary surface, whose throughput is exactly 1
+            const float4 t = c.w != 0.0f ? make_float4(1.f, 1.f, 1.f, 0.f) : shadowQueue.throughput[j];
+            rad.x += t.x * (c.x * vis * fp.solarInvPdf);
+            rad.y += t.y * (c.y * vis * fp.solarInvPdf);
+            rad.z += t.z * (c.z * vis * fp.solarInvPdf);
+            radiance[idx] = rad;
+            return false;
+        }
         rad.x += c.x * vis * fp.solarInvPdf;
         rad.y += c.y * vis * fp.solarInvPdf;
         rad.z += c.z * vis * fp.solarInvPdf;

@@ -585,19 +585,21 @@ __device__ __forceinline__ void traceRays(
 #undef RF_ANY_HIT
 }
 
-// offsetRay, wgsl:523-544 / ray_intersection.cpp:17-35.
-__device__ __forceinline__ float offsetRayComponent(const float p, const float n)
+// offsetRay, wgsl:523-544 / ray_intersection.cpp:17-35 (INT_SCALE 256, FLOAT_SCALE 1/65536); the deferred
+// renderer's offsetPosition (deferred_renderer_lighting_pass.wgsl:500-519) is the same function with INT_SCALE 1024
+// and FLOAT_SCALE 1/16384.
+__device__ __forceinline__ float offsetRayComponent(const float p, const float n, const bool deferred = false)
 {
     const float ORIGIN = 1.0f / 32.0f;
-    const float FLOAT_SCALE = 1.0f / 65536.0f;
-    const float INT_SCALE = 256.0f;
+    const float FLOAT_SCALE = deferred ? 1.0f / 16384.0f : 1.0f / 65536.0f;
+    const float INT_SCALE = deferred ? 1024.0f : 256.0f;
     const int   off = __float2int_rz(INT_SCALE * n);
     const float po = __int_as_float(__float_as_int(p) + ((p < 0.0f) ? -off : off));
     return (fabsf(p) < ORIGIN) ? (p + FLOAT_SCALE * n) : po;
 }
 
 // Hit point of an accepted triangle: p = v0 + u*e1 + v*e2, then offsetRay(p, n) (wgsl:509-516).
-__device__ __forceinline__ V3 hitPoint(const float4* __restrict__ tris, const HitRecord& hit)
+__device__ __forceinline__ V3 hitPoint(const float4* __restrict__ tris, const HitRecord& hit, const bool deferred = false)
 {
     const float4 a = ldg4(tris + 3 * hit.tri + 0);
     const float4 b = ldg4(tris + 3 * hit.tri + 1);
@@ -607,6 +609,6 @@ __device__ __forceinline__ V3 hitPoint(const float4* __restrict__ tris, const Hi
     const V3     e2 = v3(b.z, b.w, c.x);
     const V3     n = v3(c.y, c.z, c.w);
     const V3     p = (v0 + hit.u * e1) + hit.v * e2;
-    return v3(offsetRayComponent(p.x, n.x), offsetRayComponent(p.y, n.y), offsetRayComponent(p.z, n.z));
+    return v3(offsetRayComponent(p.x, n.x, deferred), offsetRayComponent(p.y, n.y, deferred), offsetRayComponent(p.z, n.z, deferred));
 }
 } // namespace rfb200

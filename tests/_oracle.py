@@ -44,6 +44,11 @@ class OracleFrame(C.Structure):
                 ("camera", C.c_float * 19), ("skyState", C.c_float * 40)]
 
 
+class OracleDeferred(C.Structure):
+    _fields_ = [("inverseViewReverseZProjection", C.c_float * 16), ("cameraEye", C.c_float * 4), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("frameCount", C.c_uint32), ("skyState", C.c_float * 40)]
+
+
 @lru_cache(maxsize=None)
 def oracle() -> C.CDLL:
     build_oracle()
@@ -62,6 +67,9 @@ def oracle() -> C.CDLL:
     lib.oracle_render_frame.restype = C.c_double
     lib.oracle_render_frame.argtypes = [C.POINTER(OracleScene), C.POINTER(OracleFrame), _P, _P, _P, C.c_int]
     lib.oracle_display.argtypes = [_P, C.c_uint64, C.c_float, C.c_float, _P]
+    lib.oracle_deferred_lighting.restype = C.c_double
+    lib.oracle_deferred_lighting.argtypes = [C.POINTER(OracleScene), C.POINTER(OracleDeferred), _P, _P, _P, _P, _P, C.c_int]
+    lib.oracle_deferred_resolve.argtypes = [_P, _P, C.c_uint64, C.c_uint32]
     return lib
 
 
@@ -203,6 +211,48 @@ class OracleRenderer:
     def display(self, exposure: float) -> np.ndarray:
         out = np.zeros((self.height, self.width), dtype=np.uint32)
         oracle().oracle_display(_ptr(self.image), self.width * self.height, float(max(self.accumulated, 1)), exposure, _ptr(out))
+        return out
+
+
+class OracleDeferredLighting:
+    """The deferred renderer's lighting + resolve passes restated (oracle.cpp, oracle_deferred_lighting / _resolve)."""
+
+    def __init__(self, pt, sky40, threads=None):
+        self.nodes = np.ascontiguousarray(pt.bvh_nodes)
+        self.pos = np.ascontiguousarray(pt.triangle_position_attributes)
+        self.vat = np.ascontiguousarray(pt.triangle_vertex_attributes)
+        self.desc, self.texels = tex_desc(pt.base_color_textures)
+        self.bn = blue_noise_rg8()
+        self.scene = OracleScene(_ptr(self.nodes), _ptr(self.pos), _ptr(self.vat), _ptr(self.desc), len(self.desc),
+                                 _ptr(self.texels), self.texels.size, _ptr(self.bn))
+        self.sky40 = np.ascontiguousarray(sky40, dtype=np.float32)
+        self.threads = threads or num_threads()
+        self.counters = np.zeros(9, dtype=np.uint64)
+        self.sample = None
+        self.accumulation = None
+
+    def render(self, inv_view_proj, eye, frame_count, albedo, normal, depth):
+        h, w = depth.shape
+        un = OracleDeferred((C.c_float * 16)(*np.asarray(inv_view_proj, dtype=np.float32).reshape(16)),
+                            (C.c_float * 4)(float(eye[0]), float(eye[1]), float(eye[2]), 1.0), w, h, frame_count, (C.c_float * 40)(*self.sky40))
+        a = np.ascontiguousarray(albedo, dtype=np.float32)
+        n = np.ascontiguousarray(normal, dtype=np.float32)
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        self.sample = np.zeros((h, w, 3), dtype=np.float32)
+        oracle().oracle_deferred_lighting(C.byref(self.scene), C.byref(un), _ptr(a), _ptr(n), _ptr(d), _ptr(self.sample), _ptr(self.counters), self.threads)
+        if self.accumulation is None or self.accumulation.shape != self.sample.shape:
+            self.accumulation = np.zeros_like(self.sample)
+        oracle().oracle_deferred_resolve(_ptr(self.sample), _ptr(self.accumulation), w * h, frame_count)
+
+    def stats(self) -> dict:
+        return {k: int(v) for k, v in zip(COUNTER_NAMES, self.counters)}
+
+    def display(self, exposure: float) -> np.ndarray:
+        h, w, _ = self.accumulation.shape
+        rgba = np.zeros((h, w, 4), dtype=np.float32)
+        rgba[..., :3] = self.accumulation
+        out = np.zeros((h, w), dtype=np.uint32)
+        oracle().oracle_display(_ptr(rgba), w * h, 1.0, exposure, _ptr(out))
         return out
 
 
