@@ -71,12 +71,13 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
         self.proc = None
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []  # (arrival time, csv line)
+        self.begin = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -84,16 +85,29 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark_begin(self):
+        """The timed region starts now (the sampler was started before the warm-up: nvidia-smi takes longer to come up
+        than a multi-GPU timed region lasts)."""
+        self.begin = time.monotonic()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        end = time.monotonic()
+        time.sleep(0.05)
         self.proc.terminate()
+        begin = self.begin if self.begin is not None else 0.0
+        inside = [line for t, line in self.lines if begin <= t <= end + 0.03]
+        note = None
+        if not inside:
+            # a region shorter than one sampling period: the samples of the warm-up steps right before it (same load)
+            inside = [line for t, line in self.lines if begin - 1.0 <= t]
+            note = "timed region shorter than the sampling period: samples taken during the warm-up steps just before it"
         sm, sm_max, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in inside:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -105,8 +119,11 @@ class ClockSampler:
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ---- the reference's CPU traversal ------------------------------------------------------------------------
@@ -256,6 +273,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         flush.zero_()
         step_device()
@@ -265,9 +284,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ren.reset_stats()
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pairs)
         e0[k].record(stream)

@@ -823,6 +823,23 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     std::memcpy(un.cameraEye, p->camera_eye, sizeof(un.cameraEye));
     un.frameCount = p->frame_count;
 
+    // device time of the passes (without the G-buffer upload), reported like the path tracer's render-pass duration
+    r->drainTimings(false);
+    rf_renderer::Timed t{};
+    if (!r->eventPool.empty())
+    {
+        t = std::move(r->eventPool.back());
+        r->eventPool.pop_back();
+    }
+    else
+    {
+        RF_CUDA(cudaEventCreate(&t.begin));
+        RF_CUDA(cudaEventCreate(&t.end));
+    }
+    t.stagesUsed = 0;
+    t.bounces = 1;
+    RF_CUDA(cudaEventRecord(t.begin, s));
+
     std::uint32_t* ctr = d.counters.ptr;
     std::uint32_t* const cursors = ctr + 2;
     const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u};
@@ -837,6 +854,8 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     launchTrace(r->variant, r->traceBlock, gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], noHandOver, r->stats.ptr);
     k_deferred_resolve<<<gridLight, BLOCK_THREADS, 0, s>>>(static_cast<std::uint32_t>(numPixels), p->frame_count, r->radiance.ptr, d.accumulation.ptr);
     RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaEventRecord(t.end, s));
+    r->pending.push_back(std::move(t));
     r->kernelLaunches += 5;
     r->frames++;
     return RF_OK;

@@ -31,5 +31,6 @@ ren.synchronize()
 dt = time.perf_counter() - t0
 s = ren.stats()
 rays = s["closest_rays"] + s["shadow_rays"]
-print(f"{w}x{h}: {dt / frames * 1e3:.2f} ms per frame end to end ({(albedo.nbytes + normal.nbytes + depth.nbytes) / 1e6:.0f} MB of G-buffer copied in per frame), "
+print(f"{w}x{h}: {s['device_ms_total'] / frames:.2f} ms per frame on the device ({rays / s['device_ms_total'] / 1e3:.0f} Mrays/s), "
+      f"{dt / frames * 1e3:.2f} ms per frame end to end ({(albedo.nbytes + normal.nbytes + depth.nbytes) / 1e6:.0f} MB of G-buffer copied in per frame), "
       f"{rays // frames} rays per frame ({s['shadow_rays'] // frames} shadow, {s['closest_rays'] // frames} closest) -> {rays / dt / 1e6:.0f} Mrays/s end to end")
