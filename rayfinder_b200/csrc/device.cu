@@ -705,7 +705,9 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         const std::uint32_t evictMax = staged ? 0u : r->effectiveEvictMax();
         std::uint32_t* const stragglerCounts = ctr + 2u * fp.numBounces + 2u;
         std::uint32_t* const stragglerCursors = ctr + 3u * fp.numBounces + 3u;
-        const auto           stragglersOf = [&](std::uint32_t k) { return StragglerBuffer{sf.stragglers.ptr, &stragglerCounts[k], r->stragglerCapacity(), evictMax}; };
+        // rounds a warp keeps its last rays before handing them over (measured: 4 lets the many short ones end in place)
+        static const std::uint32_t evictDelay = std::getenv("RF_EVICT_DELAY") ? static_cast<std::uint32_t>(std::atoi(std::getenv("RF_EVICT_DELAY"))) : 4u;
+        const auto           stragglersOf = [&](std::uint32_t k) { return StragglerBuffer{sf.stragglers.ptr, &stragglerCounts[k], r->stragglerCapacity(), evictMax, evictDelay}; };
         const auto           finishStragglers = [&](std::uint32_t k, const PathQueue& closestQueue, const PathQueue& shadowQueue) {
             if (evictMax == 0u) return;
             // persistent warps, one ray at a time each; blocks beyond the number of records exit at once
@@ -842,7 +844,7 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
 
     std::uint32_t* ctr = d.counters.ptr;
     std::uint32_t* const cursors = ctr + 2;
-    const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u};
+    const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u, 0u};
     const int gridLight = r->gridFor(8);
     const int gridTrace = r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
     RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(1) * sizeof(std::uint32_t), s));

@@ -72,6 +72,7 @@ struct StragglerBuffer
     std::uint32_t*   count;    // records appended so far (may overshoot `capacity` transiently; readers clamp)
     std::uint32_t    capacity;
     std::uint32_t    evictMax; // a warp hands its rays over once the queue is dry and it has <= evictMax of them left (0: never)
+    std::uint32_t    evictDelay; // ... and has gone through this many more loop rounds in that state: short rays end in place
 };
 
 // Work source over a plain array of `numRays` items: a device cursor advanced with one atomicAdd per warp.
@@ -452,7 +453,8 @@ __device__ __forceinline__ void traceRays(
         std::uint32_t* entries = reinterpret_cast<std::uint32_t*>(rec->stack);
         for (std::uint32_t k = 0; k < depth; ++k) entries[k] = stackLoad(stackBase + k * STACK_STRIDE);
     };
-    bool mayEvict = IO::HANDS_OVER_STRAGGLERS;
+    bool          mayEvict = IO::HANDS_OVER_STRAGGLERS;
+    std::uint32_t evictWait = 0; // rounds spent with few rays left since the queue ran dry
 #ifdef RF_TRACE_TIMELINE
     const unsigned long long tlStart = globalTimerNs();
     unsigned long long       tlDry = 0;
@@ -553,7 +555,7 @@ __device__ __forceinline__ void traceRays(
           if (mayEvict && exhausted && !gotWork)
           {
             const std::uint32_t busy = static_cast<std::uint32_t>(__popc(busyMask));
-            if (busy <= io.stragglers.evictMax)
+            if (busy <= io.stragglers.evictMax && evictWait++ >= io.stragglers.evictDelay)
             {
                 std::uint32_t base = 0;
                 if (laneId() == 0u) base = atomicAdd(io.stragglers.count, busy);
