@@ -82,7 +82,7 @@ rf_status selectDevice(int32_t device, int& outDevice, int& numSms)
 // increase along any descent (=> termination), leaf ranges lie inside the triangle array, interior
 // split axes are 0..2, and the deepest leaf fits the reference's 32-entry stack
 // (ray_intersection.cpp:148,194; wgsl:327,375).
-rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uint64_t numTriangles, bool& ordered)
+rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uint64_t numTriangles, bool& ordered, std::uint32_t* stackEntries = nullptr)
 {
     ordered = true;
     if (numNodes == 0 || numNodes >= 0x7FFFFFFFull) return setError(RF_ERROR_INVALID_ARGUMENT, "BVH must have between 1 and 2^31-1 nodes.");
@@ -128,6 +128,7 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
     }
     if (maxPending > static_cast<std::uint32_t>(RF_STACK_SIZE))
         return setError(RF_ERROR_INVALID_ARGUMENT, "BVH depth %u exceeds the traversal stack of %d entries.", maxPending, RF_STACK_SIZE);
+    if (stackEntries) *stackEntries = std::max(maxPending, 1u);
     return RF_OK;
 }
 
@@ -168,16 +169,26 @@ rf_status validateParams(const rf_render_parameters& p, std::uint32_t maxW, std:
 } // namespace
 
 // Compile-time scheduling variants of the traversal kernel, selected per launch (tuning only).
-template<int V, int BLOCK>
+template<int V, int BLOCK, int STACK = RF_STACK_SIZE>
 void launchTraceV(int grid, cudaStream_t s, const FrameParams& fp, const SceneDevice& scene, const PathQueue& closestQueue,
                   const std::uint32_t* closestCount, HitRecord* hits, const PathQueue& shadowQueue, const std::uint32_t* shadowCount,
                   float4* radiance, std::uint32_t* cursor, const StragglerBuffer& stragglers, unsigned long long* stats)
 {
-    k_trace<V, BLOCK><<<grid, BLOCK, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stragglers, stats);
+    k_trace<V, BLOCK, STACK><<<grid, BLOCK, 0, s>>>(fp, scene, closestQueue, closestCount, hits, shadowQueue, shadowCount, radiance, cursor, stragglers, stats);
 }
+// `stackEntries` = what the scene needs (validateBvh).  The default kernel (variant 3, 256 threads) exists with 23-,
+// 31- and 32-entry stacks: the smaller ones leave more of the SM's 256 KB to L1 (traversal.cuh, traceRays).
 template<typename... Args>
-void launchTrace(int variant, int block, Args&&... args)
+void launchTrace(int variant, int block, std::uint32_t stackEntries, Args&&... args)
 {
+    if (block == 256 && (variant & 15) == TRACE_DEFAULT_VARIANT && stackEntries <= 31u)
+    {
+        if (stackEntries <= 23u)
+            launchTraceV<TRACE_DEFAULT_VARIANT, 256, 23>(args...);
+        else
+            launchTraceV<TRACE_DEFAULT_VARIANT, 256, 31>(args...);
+        return;
+    }
     if (block == 64)
     {
         if ((variant & 15) == 2) launchTraceV<2, 64>(args...);
@@ -455,6 +466,13 @@ struct rf_renderer
     // Automatic scheduling, from measurements on B200 (Sponza, 8 bounces; DESIGN.md "Tails"): with more than ~0.6 M
     // paths per GPU (the 1080p frame on 1-2 GPUs) two tile sets on two streams and no hand-over are fastest; below
     // that (a 1080p frame split over 4-8 GPUs) a launch is mostly tail and one tile set with the hand-over wins.
+    std::uint32_t stackEntries = RF_STACK_SIZE; // deepest traversal stack the scene can produce (validateBvh)
+    // RF_TRACE_STACK=32 forces the reference-sized stack (A/B runs)
+    std::uint32_t traceStackEntries() const
+    {
+        static const int forced = std::getenv("RF_TRACE_STACK") ? std::atoi(std::getenv("RF_TRACE_STACK")) : 0;
+        return forced > 0 ? std::max(static_cast<std::uint32_t>(forced), stackEntries) : stackEntries;
+    }
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
@@ -476,13 +494,15 @@ extern "C" rf_status rf_renderer_create(
         return setError(RF_ERROR_INVALID_ARGUMENT, "Scene spans must be non-empty.");
     if (scene->num_position_attributes != scene->num_vertex_attributes)
         return setError(RF_ERROR_INVALID_ARGUMENT, "positionAttributes and vertexAttributes must have the same length.");
-    bool      ordered = true;
-    rf_status st = validateBvh(scene->bvh_nodes, scene->num_bvh_nodes, scene->num_position_attributes, ordered);
+    bool          ordered = true;
+    std::uint32_t stackEntries = RF_STACK_SIZE;
+    rf_status     st = validateBvh(scene->bvh_nodes, scene->num_bvh_nodes, scene->num_position_attributes, ordered, &stackEntries);
     if (st != RF_OK) return st;
     st = validateParams(desc->render_params, desc->max_framebuffer_width, desc->max_framebuffer_height);
     if (st != RF_OK) return st;
 
     auto r = std::make_unique<rf_renderer>();
+    r->stackEntries = stackEntries;
     st = selectDevice(device, r->device, r->numSms);
     if (st != RF_OK) return st;
     r->ordered = ordered;
@@ -718,7 +738,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         k_raygen<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
         // closest-hit rays of bounce 1
-        launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0],
+        launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0],
                     stragglersOf(0), r->stats.ptr);
         finishStragglers(0, sf.queues[0], sf.queues[0]);
         for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
@@ -729,7 +749,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             RF_CUDA(stageMark());
             // shadow rays of this bounce + closest-hit rays of the next one (none after the last bounce)
             const bool last = bounce == fp.numBounces;
-            launchTrace(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
+            launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
                         r->radiance.ptr, &cursors[bounce], stragglersOf(bounce), r->stats.ptr);
             finishStragglers(bounce, sf.queues[outQ], sf.queues[outQ]);
         }
@@ -850,10 +870,10 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(1) * sizeof(std::uint32_t), s));
     k_deferred_primary<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, un, d.albedo.ptr, d.normal.ptr, d.depth.ptr, queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
     // shadow rays of the G-buffer surfaces + the bounce rays
-    launchTrace(r->variant, r->traceBlock, gridTrace, s, fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[0], &ctr[0], r->radiance.ptr, &cursors[0], noHandOver, r->stats.ptr);
+    launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, s, fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[0], &ctr[0], r->radiance.ptr, &cursors[0], noHandOver, r->stats.ptr);
     k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr);
     // shadow rays of the bounce hits
-    launchTrace(r->variant, r->traceBlock, gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], noHandOver, r->stats.ptr);
+    launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], noHandOver, r->stats.ptr);
     k_deferred_resolve<<<gridLight, BLOCK_THREADS, 0, s>>>(static_cast<std::uint32_t>(numPixels), p->frame_count, r->radiance.ptr, d.accumulation.ptr);
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventRecord(t.end, s));

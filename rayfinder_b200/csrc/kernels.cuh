@@ -444,7 +444,7 @@ struct TraceIO : CursorSource
 #ifndef RF_TRACE_MIN_BLOCKS
 #define RF_TRACE_MIN_BLOCKS 4
 #endif
-template<int VARIANT, int BLOCK>
+template<int VARIANT, int BLOCK, int STACK = RF_STACK_SIZE>
 __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_trace(
     const FrameParams    fp,
     const SceneDevice    scene,
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_tr
     const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
     TraceIO io{{fetchCursor, numClosest + numShadow}, stragglers, fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance,
                   v3(fp.sky.sun_direction), blockStats};
-    traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
+    traceRays<2, VARIANT, BLOCK, TraceIO, STACK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
     __syncthreads();
     if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
     {

@@ -267,7 +267,11 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
 //   bits 0-1: node steps per warp vote minus 1 (1..4)   bit 2: triangle round tests the whole leaf (else one
 //   triangle per round)   bit 3: node step written as branches (else as selects / predication)
 constexpr int TRACE_DEFAULT_VARIANT = 3;
-template<int MODE, int VARIANT, int BLOCK, class IO>
+// STACK: entries of the per-thread traversal stack.  The reference's 32 is an upper bound; a scene whose deepest
+// interior node needs fewer (validateBvh) can run with a smaller shared-memory stack, which decides the SM's
+// shared-memory carve-out and therefore how much L1 is left for the nodes: 4 blocks x (32 x 256 x 4 B + 1 KB) need the
+// 164 KB carve-out (88 KB of L1), 31 entries fit the 132 KB one (120 KB of L1), 23 entries the 100 KB one.
+template<int MODE, int VARIANT, int BLOCK, class IO, int STACK = 32>
 __device__ __forceinline__ void traceRays(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
@@ -277,7 +281,8 @@ __device__ __forceinline__ void traceRays(
 {
     // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array (entry k of this thread
     // lives STACK_STRIDE * k bytes above stackBase; bank = lane for every k).
-    __shared__ std::uint32_t stackMem[RF_STACK_SIZE * BLOCK];
+    static_assert(STACK >= 1 && STACK <= RF_STACK_SIZE, "the reference's stack has 32 entries");
+    __shared__ std::uint32_t stackMem[STACK * BLOCK];
     constexpr std::uint32_t  STACK_STRIDE = BLOCK * 4u;
     const std::uint32_t      stackBase = static_cast<std::uint32_t>(__cvta_generic_to_shared(stackMem + threadIdx.x));
     std::uint32_t            stackTop = stackBase; // address of the next free entry
