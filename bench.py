@@ -239,7 +239,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ren.set_tile_partition(rank, world)
     stream = torch.cuda.current_stream(dev)
     ren.set_stream(stream.cuda_stream)
-    hdr = rfd.hdr_tensor(ren, w, h)
+    exchange = rfd.HdrExchange(ren, w, h, mode=os.environ.get("RF_EXCHANGE", "auto"))
+    hdr = exchange.hdr
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_hdr = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
     host_np = host_hdr.numpy()
@@ -257,12 +258,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def step_device():
         new_frame()
         ren.render()
-        rfd.reduce_hdr(hdr, dst=0)
+        exchange()
 
     def step_e2e():
         new_frame()  # host -> device: the render parameters (uniform block) travel with the launch
         ren.render()
-        rfd.reduce_hdr(hdr, dst=0)
+        exchange()
         if rank == 0:
             ren.read_hdr(host_np)  # device -> host: the HDR image
         else:
@@ -376,7 +377,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                     f"{bounces} x shade, accumulate per set)"
                                     + (f"; each trace launch hands warps left with <= {stats['evict_max']} rays to a warp-per-ray tail launch"
                                        if stats["evict_max"] else "")),
-                       "partition": f"32x32 tiles, (tx+ty) % {world}, one NCCL sum-reduce of the HDR buffer per step" if world > 1 else "single GPU"},
+                       "partition": (f"32x32 tiles, (tx+ty) % {world}; exchange per step: "
+                                     + ("owned pixels stored into rank 0's HDR buffer over NVLink peer memory by the accumulation kernel + a 4-byte "
+                                        "all-reduce as frame barrier" if exchange.mode == "p2p" else "one NCCL sum-reduce of the HDR buffer"))
+                       if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": rays_total / e2e_seconds / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": w * h * 16, "ms_per_step": 1e3 * e2e_seconds / args.steps},
@@ -392,6 +396,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                     "sample": cpu.sample_description(rows)}
         print(json.dumps(line), flush=True)
 
+    exchange.close()
     ren.close()
     if world > 1:
         dist.destroy_process_group()

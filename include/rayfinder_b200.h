@@ -244,6 +244,16 @@ uint32_t  rf_renderer_accumulated_sample_count(const rf_renderer* r);
  * bit-identical to a single-GPU frame.  Resets the accumulation. */
 rf_status rf_renderer_set_tile_partition(rf_renderer* r, uint32_t rank, uint32_t world);
 
+/* The exchange fused into the accumulation kernel (one process per GPU, same node).  The root rank exports its HDR buffer
+ * (64-byte CUDA IPC handle); every other rank maps it, and from then on its accumulation kernel also stores each owned
+ * pixel's accumulated value into the root's buffer over NVLink peer memory.  A pixel has exactly one owner, so after all
+ * ranks have finished the frame (any stream-ordered barrier, e.g. a 4-byte all-reduce) the root's buffer holds the full
+ * frame, bit-identical to the single-GPU one, without moving W x H x 16 bytes through a reduction.  The root must not
+ * restart its own accumulation (which clears the buffer) while other ranks are still writing a frame: keep the ranks in
+ * step with the barrier, as rayfinder_b200/distributed.py does.  NULL detaches. */
+rf_status rf_renderer_hdr_ipc_handle(rf_renderer* r, void* out_handle_64_bytes);
+rf_status rf_renderer_set_hdr_peer(rf_renderer* r, const void* handle_64_bytes);
+
 rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out);
 rf_status rf_renderer_reset_stats(rf_renderer* r);
 /* Per-stage CUDA-event timing (adds event records between stages; off by default). */

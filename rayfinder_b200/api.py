@@ -362,6 +362,14 @@ class ReferencePathTracer:
         check(lib().rf_renderer_read_deferred(self._handle, _ptr(sample), _ptr(accumulation), _ptr(display)))
         return sample, accumulation, display
 
+    def hdr_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().rf_renderer_hdr_ipc_handle(self._handle, buf))
+        return buf.raw
+
+    def set_hdr_peer(self, handle: "bytes | None") -> None:
+        check(lib().rf_renderer_set_hdr_peer(self._handle, C.create_string_buffer(handle, 64) if handle is not None else None))
+
     def hdr_device_ptr(self) -> int:
         return lib().rf_renderer_hdr_device_ptr(self._handle) or 0
 

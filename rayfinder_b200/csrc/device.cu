@@ -286,6 +286,8 @@ struct rf_renderer
         std::uint32_t               width = 0, height = 0;
         float                       exposure = 1.0f;
     } deferred;
+    float4*       peerImage = nullptr;  // the root rank's HDR buffer mapped through CUDA IPC (rf_renderer_set_hdr_peer)
+    bool          exportedRoot = false; // this renderer's HDR buffer is the target of the other ranks' stores
     std::uint64_t kernelLaunches = 0;   // kernels launched by render() since the last reset_stats
     int         numSubFrames = 2;       // in effect (updateTiles)
     int         requestedSubFrames = 0; // 0: automatic
@@ -333,6 +335,7 @@ struct rf_renderer
             if (sf.done) cudaEventDestroy(sf.done);
         }
         if (forkEvent) cudaEventDestroy(forkEvent);
+        if (peerImage) cudaIpcCloseMemHandle(peerImage);
     }
 
     void drainTimings(bool wait)
@@ -672,9 +675,12 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
 
     RF_CUDA(cudaEventRecord(t.begin, s));
     const std::uint64_t numPixels = static_cast<std::uint64_t>(fp.width) * fp.height;
-    if (r->accumulated == 0)
+    const bool restart = r->accumulated == 0;
+    if (restart && !(r->exportedRoot && r->world > 1))
     {
-        // fsMain:45-47: imageBuffer[idx] = vec3(0f) on the first sample (also clears non-owned tiles).
+        // fsMain:45-47: imageBuffer[idx] = vec3(0f) on the first sample; k_accumulate does that for the owned pixels, this
+        // clears the others (what a sum-reduce over ranks needs).  The root of a peer-memory exchange must NOT clear them:
+        // they belong to the other ranks, which overwrite them every frame and may already be writing.
         RF_CUDA(cudaMemsetAsync(r->image.ptr, 0, numPixels * sizeof(float4), s));
     }
     RF_CUDA(cudaEventRecord(r->forkEvent, s));
@@ -701,7 +707,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             k_mega_init<<<1, 1, 0, ss>>>(sf.control.ptr, &ctr[0]);
             launchMega(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], sf.meta.ptr, r->radiance.ptr, sf.control.ptr, sf.ready.ptr,
                        sf.log2Cap, r->stats.ptr);
-            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, r->peerImage, restart);
             r->kernelLaunches += 4;
             if (std::getenv("RF_DEBUG_MEGA"))
             {
@@ -754,7 +760,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             finishStragglers(bounce, sf.queues[outQ], sf.queues[outQ]);
         }
         RF_CUDA(stageMark());
-        k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr);
+        k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, r->peerImage, restart);
         // raygen + (numBounces + 1) traversal launches (+ their straggler follow-ups) + numBounces shades + accumulate
         r->kernelLaunches += 2ull + (fp.numBounces + 1ull) * (evictMax != 0u ? 2ull : 1ull) + fp.numBounces;
         RF_CUDA(stageMark());
@@ -1066,6 +1072,45 @@ extern "C" std::uint32_t rf_debug_timeline_read(void* dst, std::uint32_t capacit
     return n;
 }
 #endif
+
+// ---- multi-GPU exchange over NVLink peer memory -----------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "rf_renderer_hdr_ipc_handle hands out 64 bytes");
+
+extern "C" rf_status rf_renderer_hdr_ipc_handle(rf_renderer* r, void* outHandle64)
+{
+    if (!r || !outHandle64) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_hdr_ipc_handle: null argument");
+    RF_CUDA(cudaSetDevice(r->device));
+    cudaIpcMemHandle_t h;
+    RF_CUDA(cudaIpcGetMemHandle(&h, r->image.ptr));
+    std::memcpy(outHandle64, &h, sizeof(h));
+    r->exportedRoot = true;
+    return RF_OK;
+}
+
+extern "C" rf_status rf_renderer_set_hdr_peer(rf_renderer* r, const void* handle64)
+{
+    if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_hdr_peer: null renderer");
+    RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    for (auto& sf : r->sub)
+        if (sf.stream) RF_CUDA(cudaStreamSynchronize(sf.stream));
+    if (r->peerImage)
+    {
+        RF_CUDA(cudaIpcCloseMemHandle(r->peerImage));
+        r->peerImage = nullptr;
+    }
+    if (!handle64)
+    {
+        r->exportedRoot = false;
+        return RF_OK;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    void* mapped = nullptr;
+    RF_CUDA(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    r->peerImage = static_cast<float4*>(mapped);
+    return RF_OK;
+}
 
 extern "C" rf_status rf_renderer_set_tail_policy(rf_renderer* r, std::int32_t evictMax)
 {

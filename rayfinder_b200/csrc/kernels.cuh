@@ -527,11 +527,16 @@ __global__ void __launch_bounds__(STRAGGLER_BLOCK_THREADS) k_trace_stragglers(
 }
 
 // ---------------------------------------------------------------------------------------------
+// `peerImage` (multi-GPU, may be null): the HDR buffer of the root rank, mapped over NVLink peer memory.  Every pixel has
+// exactly one owner, so writing the owner's accumulated value there IS the per-frame exchange: accumulate and exchange in
+// one kernel, 16 B per owned pixel over NVLink, instead of a sum-reduce of W x H x 16 B full of zeros.
 __global__ void __launch_bounds__(BLOCK_THREADS) k_accumulate(
     const FrameParams fp,
     const std::uint32_t* __restrict__ ownedTiles,
     const float4* __restrict__ radiance,
-    float4*           image)
+    float4*           image,
+    float4*           peerImage,
+    const bool        restart) // first sample of an accumulation: imageBuffer[idx] = vec3(0f) (fsMain:45-47)
 {
     const std::uint32_t total = fp.numOwnedTiles * TILE_PIXELS;
     for (std::uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x)
@@ -540,9 +545,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_accumulate(
         if (!slotToPixel(fp, ownedTiles, slot, px, py)) continue;
         const std::uint32_t idx = py * fp.width + px;
         const float4        r = radiance[idx];
-        float4              im = image[idx];
+        float4              im = restart ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : image[idx];
         im.x += r.x, im.y += r.y, im.z += r.z;
         image[idx] = im;
+        if (peerImage) peerImage[idx] = im;
     }
 }
 

@@ -1,5 +1,7 @@
-"""Multi-GPU plumbing of the render path: one process per GPU, frames partitioned by 32x32 pixel tile,
-one sum-reduce of the HDR accumulation buffer to rank 0 (NCCL over NVLink; gloo on CPU for the tests).
+"""Multi-GPU plumbing of the render path: one process per GPU, frames partitioned by 32x32 pixel tile, and one
+exchange step per frame that brings the HDR accumulation buffer together on rank 0 — either a sum-reduce (NCCL over
+NVLink; gloo on CPU for the tests) or, fused into the accumulation kernel, direct stores of every owned pixel into rank
+0's buffer over NVLink peer memory (`HdrExchange`, mode "p2p").
 
 The reference is single-GPU; this is the only exchange step the path has.  Tiles are
 disjoint and every non-owned pixel is exactly 0.0f, so the fp32 sum is exact and the reduced image is
@@ -45,3 +47,60 @@ def reduce_hdr(tensor, dst: int = 0, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return tensor
+
+
+class HdrExchange:
+    """The per-frame exchange step of the multi-GPU path, called right after ``renderer.render()`` on every rank.
+
+    mode "nccl": one ``reduce(SUM)`` of the W x H x 16-byte HDR buffer to ``root`` (what BASELINE.json's north_star names).
+    mode "p2p":  the exchange is fused into the accumulation kernel — the root exports its HDR buffer through CUDA IPC, the
+                 other ranks map it, and their ``k_accumulate`` stores each owned pixel's accumulated value straight into
+                 it over NVLink peer memory; what is left per frame is a 4-byte all-reduce that orders "all ranks have
+                 finished the frame" before the root uses the image (and keeps the ranks in step).  16 bytes per owned
+                 pixel cross NVLink instead of W x H x 16 bytes of mostly zeros going through a reduction.
+    mode "auto": "p2p" if every rank could map the root's buffer, else "nccl".
+    Both produce the single-GPU image bit for bit on the root (tools/check_multigpu.py)."""
+
+    def __init__(self, renderer, width: int, height: int, mode: str = "auto", root: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.renderer, self.root, self.group = renderer, root, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.hdr = hdr_tensor(renderer, width, height)
+        self.mode = "nccl"
+        if self.world == 1 or mode == "nccl":
+            return
+        handle = [renderer.hdr_ipc_handle() if self.rank == root else None]
+        dist.broadcast_object_list(handle, src=root, group=group)
+        ok = torch.ones(1, dtype=torch.int32, device=self.hdr.device)
+        if self.rank != root:
+            try:
+                renderer.set_hdr_peer(handle[0])
+            except Exception:  # no peer access between the two devices: every rank falls back together
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            self.mode = "p2p"
+            self._token = torch.zeros(1, dtype=torch.int32, device=self.hdr.device)
+        else:
+            renderer.set_hdr_peer(None)
+            if mode == "p2p":
+                raise RuntimeError("HdrExchange: peer-memory exchange requested but a rank could not map the root's HDR buffer")
+
+    def __call__(self):
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return self.hdr
+        if self.mode == "p2p":
+            dist.all_reduce(self._token, group=self.group)  # stream-ordered after this rank's kernels: the frame barrier
+        else:
+            reduce_hdr(self.hdr, dst=self.root, group=self.group)
+        return self.hdr
+
+    def close(self):
+        if self.mode == "p2p":
+            self.renderer.set_hdr_peer(None)
+            self.mode = "nccl"

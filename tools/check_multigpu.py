@@ -4,8 +4,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tools/check_multigpu.py [width height bounces]
 
-Every rank renders its tiles of one Sponza frame, the HDR buffers are sum-reduced to rank 0 with NCCL, and
-rank 0 compares the result bit for bit with a single-GPU render of the whole frame (BASELINE.json
+Every rank renders its tiles of a Sponza frame, the HDR buffer is brought together on rank 0 with each exchange mode
+(NCCL sum-reduce; stores over NVLink peer memory fused into the accumulation kernel), and rank 0 compares the result bit
+for bit with a single-GPU render of the whole frame (BASELINE.json
 configs[3] at 3840x2160 by default)."""
 import os
 import sys
@@ -34,21 +35,34 @@ def main():
     ren = rf.ReferencePathTracer(params, (w, h), rf.SceneArrays.from_pt(pt), device=local)
     ren.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     ren.set_tile_partition(rank, world)
-    ren.render()
-    hdr = rfd.hdr_tensor(ren, w, h)
-    rfd.reduce_hdr(hdr, dst=0)
-    torch.cuda.synchronize(dev)
-    paths = torch.tensor([ren.stats()["paths"]], dtype=torch.int64, device=dev)
-    dist.all_reduce(paths)
+    results = {}
+    for mode in ("nccl", "p2p"):
+        exchange = rfd.HdrExchange(ren, w, h, mode=mode)
+        for frame in range(2):  # two frames: the second restarts the accumulation while the buffers are in use
+            params.exposure = 0.25 + 0.1 * frame
+            ren.set_render_parameters(params)
+            ren.reset_stats()
+            ren.render()
+            hdr = exchange()
+        torch.cuda.synchronize(dev)
+        paths = torch.tensor([ren.stats()["paths"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(paths)
+        if rank == 0:
+            results[exchange.mode] = (hdr.cpu().numpy().copy(), int(paths[0]))
+        dist.barrier()
+        exchange.close()
     if rank == 0:
-        reduced = hdr.cpu().numpy().copy()
         ren.set_tile_partition(0, 1)
+        params.exposure = 0.9
+        ren.set_render_parameters(params)
         ren.render()
         single, _ = ren.read_hdr()
-        same = np.array_equal(reduced.view(np.uint32), single.view(np.uint32))
-        print(f"world={world} {w}x{h} bounces={bounces}: paths={int(paths[0])} (expected {w * h}), "
-              f"reduced image bit-identical to single GPU: {same}", flush=True)
-        assert same and int(paths[0]) == w * h
+        for mode, (image, paths) in results.items():
+            same = np.array_equal(image.view(np.uint32), single.view(np.uint32))
+            print(f"world={world} {w}x{h} bounces={bounces} exchange={mode}: paths={paths} (expected {w * h}), "
+                  f"image on rank 0 bit-identical to single GPU: {same}", flush=True)
+            assert same and paths == w * h
+        assert "p2p" in results or world == 1, "peer-memory exchange was not available"
     dist.barrier()
     dist.destroy_process_group()
 
