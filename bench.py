@@ -75,6 +75,20 @@ class ClockSampler:
         self.begin = None
 
     def start(self):
+        # NVML in-process (a sample every 2 ms) when available; the nvidia-smi loop otherwise.
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)  # probe
+            self.stop_flag = threading.Event()
+            self.proc = "nvml"
+            threading.Thread(target=self._pump_nvml, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu_index)],
@@ -83,9 +97,39 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _physical_index(self) -> int:
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            ids = [x.strip() for x in visible.split(",") if x.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.monotonic(), line.strip()))
+
+    def _pump_nvml(self):
+        n = self.nvml
+        flags = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
+        try:
+            sm_max = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            sm_max = 0
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                # same 9-column layout as the nvidia-smi query
+                cols = [str(self.gpu_index), str(sm), str(sm_max), "", hex(mask)] + ["Active" if mask & bit else "Not Active" for _, bit in flags]
+                self.lines.append((time.monotonic(), ",".join(cols)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def mark_begin(self):
         """The timed region starts now (the sampler was started before the warm-up: nvidia-smi takes longer to come up
@@ -96,8 +140,11 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         end = time.monotonic()
-        time.sleep(0.05)
-        self.proc.terminate()
+        if self.proc == "nvml":
+            self.stop_flag.set()
+        else:
+            time.sleep(0.05)
+            self.proc.terminate()
         begin = self.begin if self.begin is not None else 0.0
         inside = [line for t, line in self.lines if begin <= t <= end + 0.03]
         note = None
@@ -120,7 +167,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
-               "samples": len(sm), "reasons": sorted(reasons)}
+               "samples": len(sm), "reasons": sorted(reasons), "source": "nvml" if self.proc == "nvml" else "nvidia-smi"}
         if note:
             out["note"] = note
         return out
