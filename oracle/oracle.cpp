@@ -8,6 +8,9 @@
 //   Oracle B  pt/reference_path_tracer.wgsl:34-616 (fsMain minus the display transform, plus the
 //             display transform separately) with the host-side packing of
 //             pt/reference_path_tracer.cpp:168-184 (blue noise /255) and :209-270 (texture descriptors)
+//   Oracle C  pt/deferred_renderer_lighting_pass.wgsl:96-236,497-519 (lighting pass: main, worldFromUv, surfaceColor,
+//             lightSample, skyRadiance with the solar disk, offsetPosition) and
+//             pt/deferred_renderer_resolve_pass.wgsl:34-50 (moving average), on a caller-supplied G-buffer
 // Strict fp32: compiled with -ffp-contract=off, every expression in the reference's operand order;
 // vector helpers follow glm 0.9.9.8's scalar formulas (dot = (x+y)+z, normalize = v * (1/sqrt(dot))).
 // WGSL builtins whose rounding the WGSL spec leaves open (dot/normalize/mat*vec summation order,
@@ -22,6 +25,8 @@
 //     test or golden image for it => RADIANCE PARITY IS UNPINNED against a real
 //     reference build.  Its traversal/triangle arithmetic is the pinned Oracle A code; its sky
 //     evaluation is checked against the reference's sky_state_radiance (hw_skymodel.c:182-223).
+//   * Oracle C: same situation as Oracle B (WGSL compute pass, no reference test or golden image) => PARITY UNPINNED
+//     against a real reference build; it shares Oracle A's pinned traversal/triangle code and Oracle B's helpers.
 #include <atomic>
 #include <bit>
 #include <chrono>
