@@ -251,7 +251,7 @@ def run_reference(args, rank: int):
     value = rays / secs / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "Sponza.pt baked from the reference's assets/Sponza.glb",
         "config": {"workload": workload_name(scene_name, args.width, args.height, args.bounces),
                    "note": "reference CPU path = bvh-visualizer traversal of the primary rays (the reference has no CPU path tracer)"},
