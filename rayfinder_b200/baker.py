@@ -24,7 +24,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .api import (POSITION_ATTRIBUTE_DTYPE, POSITIONS_DTYPE, VERTEX_ATTRIBUTES_DTYPE, PtFormat, build_bvh,
+from .api import (POSITION_ATTRIBUTE_DTYPE, POSITIONS_DTYPE, VERTEX_ATTRIBUTES_DTYPE, PtFormat, build_bvh, build_bvh_device,
                   reorder_attributes)
 
 f32 = np.float32
@@ -200,8 +200,10 @@ def load_gltf_model(path):
     return [meshes[i] for i in order], textures
 
 
-def bake(gltf_path) -> PtFormat:
-    """``PtFormat(gltfPath)``."""
+def bake(gltf_path, bvh_device: "int | None" = None) -> PtFormat:
+    """``PtFormat(gltfPath)``.  ``bvh_device``: build the BVH on that CUDA device (``rf_build_bvh_device``, byte-identical
+    to the host builder and ~20x faster on Sponza) instead of on the host (``rf_build_bvh``, the default: the baker also
+    runs where there is no GPU)."""
     meshes, textures = load_gltf_model(gltf_path)
 
     # FlattenedModel (flattened_model.cpp:8-46)
@@ -210,7 +212,10 @@ def bake(gltf_path) -> PtFormat:
     uvs = np.concatenate([m["tex_coords"][m["indices"]].reshape(-1, 3, 2) for m in meshes]).astype(f32)
     tex = np.concatenate([np.full(m["indices"].size // 3, m["texture"], dtype=np.uint32) for m in meshes])
 
-    nodes, tri_idx = build_bvh(pos)
+    if bvh_device is None:
+        nodes, tri_idx = build_bvh(pos)
+    else:
+        nodes, tri_idx, _ = build_bvh_device(pos, bvh_device)
     pos, nrm, uvs, tex = (reorder_attributes(a, tri_idx) for a in (pos, nrm, uvs, tex))
 
     pt = PtFormat()
