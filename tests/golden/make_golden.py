@@ -11,6 +11,9 @@
   ref_cameras.npz            createCamera outputs of the reference's camera.cpp
   oracle_duck_hdr.npz        Oracle B (oracle/oracle.cpp) HDR sums for a small Duck render: a regression pin of
                              the restatement itself (NOT a reference output; radiance parity is unpinned)
+  oracle_duck_deferred.npz   Oracle C (deferred lighting + resolve passes) on a small Duck G-buffer, two frames: inputs and
+                             outputs, again a regression pin of the restatement (python make_golden.py --deferred-only
+                             regenerates just this one)
 """
 import lzma
 import sys
@@ -100,5 +103,30 @@ def main():
     print("oracle duck hdr: mean", float(orc.image[..., :3].mean()), orc.stats())
 
 
+def deferred_pin(pt):
+    from test_gpu_deferred import make_gbuffer
+
+    w, h = 64, 48
+    lo, hi = pt.bvh_nodes["aabb_min"][0].astype(np.float64), pt.bvh_nodes["aabb_max"][0].astype(np.float64)
+    centre = 0.5 * (lo + hi)
+    eye = centre + np.array([0.9, 0.5, 1.1]) * (hi - lo).max()
+    inv, albedo, normal, depth = make_gbuffer(pt, w, h, eye, centre, seed=3)
+    sky = rf.sky_state(rf.Sky(turbidity=2.0, sun_zenith_degrees=35.0, sun_azimuth_degrees=20.0))
+    orc = O.OracleDeferredLighting(pt, sky, threads=1)
+    out = {"inv": inv, "eye": eye.astype(np.float32), "albedo": albedo[..., :3].astype(np.float32), "normal": normal[..., :3].astype(np.float32),
+           "depth": depth, "sky": sky}
+    for frame in (0, 5):
+        orc.render(inv, eye.astype(np.float32), frame, albedo, normal, depth)
+        out[f"sample_{frame}"] = orc.sample.copy()
+        out[f"accumulation_{frame}"] = orc.accumulation.copy()
+    out["counters"] = orc.counters
+    np.savez_compressed(G / "oracle_duck_deferred.npz", **out)
+    print("oracle duck deferred: surface texels", int((depth != 0).sum()), orc.stats())
+
+
 if __name__ == "__main__":
-    main()
+    if "--deferred-only" in sys.argv:
+        deferred_pin(rf.PtFormat.loads(O.duck_pt_bytes()))
+    else:
+        main()
+        deferred_pin(rf.PtFormat.loads(O.duck_pt_bytes()))

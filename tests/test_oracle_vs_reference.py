@@ -121,6 +121,25 @@ def test_oracle_b_regression_pin(duck_pt, golden):
     assert O.rmse(orc.image, g["image"]) < 1e-6  # libm may differ between boxes by an ulp in the sky term
 
 
+def test_oracle_c_regression_pin(duck_pt, golden):
+    """Oracle C (deferred lighting + resolve passes) reproduces its committed output on the committed G-buffer
+    (restatement regression pin; not a reference output)."""
+    g = golden["oracle_duck_deferred"]
+    h, w = g["depth"].shape
+    albedo = np.zeros((h, w, 4), dtype=np.float32)
+    normal = np.zeros((h, w, 4), dtype=np.float32)
+    albedo[..., :3], normal[..., :3] = g["albedo"], g["normal"]
+    orc = O.OracleDeferredLighting(duck_pt, g["sky"])
+    for frame in (0, 5):
+        orc.render(g["inv"], g["eye"], frame, albedo, normal, g["depth"])
+        assert O.rmse(orc.sample, g[f"sample_{frame}"]) < 1e-6  # libm may differ between boxes by an ulp in the sky term
+        assert O.rmse(orc.accumulation, g[f"accumulation_{frame}"]) < 1e-6
+    assert np.array_equal(orc.counters, g["counters"])
+    # frame 5 is 0.1 * sample + 0.9 * the frame-0 accumulation (deferred_renderer_resolve_pass.wgsl:44-46)
+    expected = np.float32(0.1) * g["sample_5"] + np.float32(0.9) * g["accumulation_0"]
+    assert np.array_equal(expected, g["accumulation_5"])
+
+
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
 def test_oracle_matches_reference_on_random_rays(duck_pt):
     rng = np.random.default_rng(11)
