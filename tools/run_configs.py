@@ -25,12 +25,41 @@ import rayfinder_b200 as rf  # noqa: E402
 from rayfinder_b200 import assets as rfa  # noqa: E402
 
 
+def run_sweep(ren, quick):
+    """configs[4], single-GPU part: square frames x bounce counts, automatic schedule."""
+    sweep = []
+    for size in ((256, 1024) if quick else (256, 512, 1024, 2048, 4096)):
+        for b in (1, 2, 4, 8, 16):
+            params = rf.RenderParameters((size, size), rf.fly_camera(size, size), rf.SamplingParams(1, b), rf.Sky(), 0.25)
+            frames = 5
+            for k in range(frames + 1):
+                if k == 1:
+                    ren.reset_stats()
+                params.exposure = 0.25 + 0.01 * k
+                ren.set_render_parameters(params)
+                ren.render()
+            s = ren.stats()
+            rays = (s["closest_rays"] + s["shadow_rays"]) / frames
+            sweep.append({"size": size, "bounces": b, "ms_per_frame": s["device_ms_total"] / frames, "rays_per_frame": rays,
+                          "mrays_s": rays / (s["device_ms_total"] / frames) / 1e3, "sub_frames": s["sub_frames"], "evict_max": s["evict_max"]})
+            print("sweep", sweep[-1], flush=True)
+    return sweep
+
+
 def main():
     quick = "--quick" in sys.argv
+    sweep_only = "--sweep-only" in sys.argv  # just configs[4]'s single-GPU sweep -> gpurun_out/sweep_1gpu.json
     pt = rfa.load_scene("Sponza")
     scene = rf.SceneArrays.from_pt(pt)
     sky = rf.sky_state(rf.Sky())
     out = {"scene": "Sponza.pt", "gpu": "B200", "host_threads": O.num_threads()}
+    if sweep_only:
+        params = rf.RenderParameters((1920, 1080), rf.fly_camera(1920, 1080), rf.SamplingParams(1, 8), rf.Sky(), 0.25)
+        ren = rf.ReferencePathTracer(params, (4096, 4096), scene)
+        out["config4_sweep_1gpu"] = run_sweep(ren, False)
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        (ROOT / "gpurun_out" / "sweep_1gpu.json").write_text(json.dumps(out, indent=1))
+        return
 
     # ---- configs[1] ------------------------------------------------------------------------------------
     w, h, bounces = 1920, 1080, 8
@@ -83,24 +112,7 @@ def main():
         "convergence_rmse_of_k_spp_mean_vs_final": {str(k): float(np.sqrt(np.mean((v - final) ** 2))) for k, v in running.items() if k < spp}}
     print("configs[2]", json.dumps(out[f"config2_1080p_{spp}spp_8b"]), flush=True)
 
-    # ---- configs[4], single-GPU part ------------------------------------------------------------------------
-    sweep = []
-    for size in ((256, 1024) if quick else (256, 512, 1024, 2048, 4096)):
-        for b in (1, 2, 4, 8, 16):
-            params = rf.RenderParameters((size, size), rf.fly_camera(size, size), rf.SamplingParams(1, b), rf.Sky(), 0.25)
-            frames = 5
-            for k in range(frames + 1):
-                if k == 1:
-                    ren.reset_stats()
-                params.exposure = 0.25 + 0.01 * k
-                ren.set_render_parameters(params)
-                ren.render()
-            s = ren.stats()
-            rays = (s["closest_rays"] + s["shadow_rays"]) / frames
-            sweep.append({"size": size, "bounces": b, "ms_per_frame": s["device_ms_total"] / frames, "rays_per_frame": rays,
-                          "mrays_s": rays / (s["device_ms_total"] / frames) / 1e3})
-            print("sweep", sweep[-1], flush=True)
-    out["config4_sweep_1gpu"] = sweep
+    out["config4_sweep_1gpu"] = run_sweep(ren, quick)
     if not quick:
         (ROOT / "profiles" / "r01_configs.json").write_text(json.dumps(out, indent=1))
 
