@@ -102,5 +102,8 @@ class HdrExchange:
 
     def close(self):
         if self.mode == "p2p":
-            self.renderer.set_hdr_peer(None)
+            import torch.distributed as dist
+
+            self.renderer.set_hdr_peer(None)  # peers unmap the root's buffer, the root stops skipping its clear
+            dist.barrier(group=self.group)    # ... before the root may free it
             self.mode = "nccl"
