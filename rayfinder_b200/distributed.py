@@ -61,16 +61,20 @@ class HdrExchange:
     mode "auto": "p2p" if every rank could map the root's buffer, else "nccl".
     Both produce the single-GPU image bit for bit on the root (tools/check_multigpu.py)."""
 
-    def __init__(self, renderer, width: int, height: int, mode: str = "auto", root: int = 0, group=None):
+    def __init__(self, renderer, width: int, height: int, mode: str = "auto", root: int = 0, group=None, tensor=None):
+        """``tensor``: exchange this (height, width, 4) tensor instead of the renderer's device buffer — host tensors with the
+        gloo backend in the CPU tests; only the reduce is possible then."""
         import torch
         import torch.distributed as dist
 
         self.renderer, self.root, self.group = renderer, root, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.hdr = hdr_tensor(renderer, width, height)
+        self.hdr = tensor if tensor is not None else hdr_tensor(renderer, width, height)
         self.mode = "nccl"
-        if self.world == 1 or mode == "nccl":
+        if tensor is not None and mode == "p2p":
+            raise ValueError("HdrExchange: the peer-memory exchange needs the renderer's device buffer")
+        if self.world == 1 or mode == "nccl" or tensor is not None:
             return
         handle = [renderer.hdr_ipc_handle() if self.rank == root else None]
         dist.broadcast_object_list(handle, src=root, group=group)

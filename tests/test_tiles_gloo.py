@@ -35,7 +35,12 @@ def _worker(rank: int, world: int, port: int, out_path: str):
         assert np.all(orc.image[owner != rank] == 0.0)  # non-owned pixels are exactly zero
         assert orc.stats()["paths"] == SPP * rfd.owned_pixel_count(W, H, rank, world)
         t = torch.from_numpy(orc.image)
-        rfd.reduce_hdr(t, dst=0)
+        exchange = rfd.HdrExchange(None, W, H, mode="auto", tensor=t)  # host tensor: the reduce, whatever mode is asked for
+        assert exchange.mode == "nccl" and exchange.world == world and exchange.rank == rank
+        assert exchange() is t
+        exchange.close()
+        with pytest.raises(ValueError):
+            rfd.HdrExchange(None, W, H, mode="p2p", tensor=t)
         counters = torch.from_numpy(orc.counters.astype(np.int64))
         dist.all_reduce(counters)
         if rank == 0:
