@@ -135,7 +135,8 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
 // Scheduling knobs of the persistent traversal loop; RF_TRI_MIN / RF_REFILL_MIN override for sweeps.
 TraceTuning defaultTuning()
 {
-    TraceTuning t{4u, 4u};
+    TraceTuning t{4u, 4u, 16u};
+    if (const char* e = std::getenv("RF_MEGA_SHADE_WAIT")) t.shadeWait = static_cast<std::uint32_t>(std::max(0, std::atoi(e)));
     if (const char* e = std::getenv("RF_TRI_MIN")) t.triMin = static_cast<std::uint32_t>(std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("RF_REFILL_MIN")) t.refillMin = static_cast<std::uint32_t>(std::max(1, std::atoi(e)));
     return t;

@@ -308,7 +308,7 @@ __device__ __forceinline__ void megaShadeLoop(
             __nanosleep(500);
             continue;
         }
-        if (avail < 32u && alive != 0u && waited < 16u)
+        if (avail < 32u && alive != 0u && waited < scene.tuning.shadeWait)
         {
             // let the batch fill for up to ~8 us: a dense batch costs the same as a sparse one
             ++waited;

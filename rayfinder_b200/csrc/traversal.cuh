@@ -102,6 +102,7 @@ struct TraceTuning
 {
     std::uint32_t triMin;    // run a triangle round once this many lanes have a triangle pending
     std::uint32_t refillMin; // refill once this many lanes are idle
+    std::uint32_t shadeWait; // persistent kernel: 0.5 us naps the shading warp takes to let a batch of 32 fill (mega.cuh)
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
