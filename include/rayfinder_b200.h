@@ -301,7 +301,8 @@ rf_status rf_renderer_render_deferred_lighting(
     const float*                       gbuffer_normal,
     const float*                       gbuffer_depth);
 /* sampleBuffer and accumulationBuffer (3 floats per pixel) and the resolve pass's BGRA8 output of the last deferred
- * frame; each pointer may be NULL. */
+ * frame; each pointer may be NULL.  The sample buffer shares the renderer's per-frame radiance scratch: read it before the
+ * next rf_renderer_render / rf_renderer_render_deferred_lighting call (the accumulation buffer and the display persist). */
 rf_status rf_renderer_read_deferred(rf_renderer* r, float* sample_rgb, float* accumulation_rgb, uint32_t* display_bgra8);
 
 /* ---- the CPU traversal twin: nlrs::rayIntersectBvh (common/ray_intersection.hpp:43-49) --------- */
