@@ -91,6 +91,54 @@ def test_build_bvh_bit_identical_to_reference(duck_pt):
         assert np.array_equal(idx, ref_idx)
 
 
+def _assert_host_bvh_equals_reference(t):
+    t = np.ascontiguousarray(t, dtype=np.float32).reshape(-1, 9)
+    h = O.ref().ref_bvh_build(O._ptr(t), t.shape[0])
+    n = O.ref().ref_bvh_num_nodes(h)
+    ref_nodes = np.zeros(n, dtype=rf.BVH_NODE_DTYPE)
+    ref_idx = np.zeros(t.shape[0], dtype=np.uint64)
+    O.ref().ref_bvh_copy(h, O._ptr(ref_nodes), O._ptr(ref_idx))
+    O.ref().ref_bvh_free(h)
+    nodes, idx = rf.build_bvh(t.reshape(-1, 3, 3))
+    assert nodes.tobytes() == ref_nodes.tobytes()
+    assert np.array_equal(idx, ref_idx)
+    return nodes
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_build_bvh_bit_identical_to_reference_on_soups():
+    """The soups tests/test_gpu_bvh_build.py feeds the GPU builder, here against the reference's own bvh.cpp: random
+    clouds, coarse grids with -0.0f / +0.0f mixed in and boxes flat at zero (the sequential min/max folds decide which
+    zero a box keeps), more than 255 identical centroids (one leaf), and SAH-says-leaf above 255 primitives (forced
+    splits).  The host builder is the GPU builder's yardstick, so it is pinned on the same cases."""
+    for n in (1, 2, 3, 4, 7, 33, 257, 1000, 20000):
+        rng = np.random.default_rng(n)
+        centres = rng.uniform(-10, 10, size=(n, 1, 3))
+        _assert_host_bvh_equals_reference(centres + rng.normal(scale=0.3, size=(n, 3, 3)))
+    rng = np.random.default_rng(11)
+    for n, grid in ((300, 2), (5000, 3), (20000, 8)):
+        tris = rng.integers(-grid, grid + 1, size=(n, 3, 3)).astype(np.float32)
+        neg = rng.random(size=tris.shape) < 0.5
+        tris = np.where((tris == 0) & neg, np.float32(-0.0), tris).astype(np.float32)
+        flat = rng.random(n) < 0.3
+        tris[flat, :, 1] = np.where(rng.random((flat.sum(), 3)) < 0.5, np.float32(-0.0), np.float32(0.0))
+        _assert_host_bvh_equals_reference(tris)
+    rng = np.random.default_rng(3)
+    same = np.tile(rng.normal(size=(1, 3, 3)), (700, 1, 1)).astype(np.float32)
+    nodes = _assert_host_bvh_equals_reference(same)
+    assert len(nodes) == 1 and nodes["triangle_count"][0] == 700
+    big = (rng.normal(scale=100.0, size=(3000, 3, 3)) + rng.normal(scale=0.01, size=(3000, 1, 3))).astype(np.float32)
+    nodes = _assert_host_bvh_equals_reference(big)
+    assert nodes["triangle_count"].max() <= 255
+    _assert_host_bvh_equals_reference(np.concatenate([same, big]))
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_build_bvh_bit_identical_to_reference_on_sponza(sponza_pt):
+    tris = O.triangles9(sponza_pt)
+    _assert_host_bvh_equals_reference(tris[np.random.default_rng(5).permutation(len(tris))])
+
+
 def test_pt_round_trip_is_byte_exact(duck_pt, tmp_path):
     """reference tests/pt_format.cpp:18-178: serialize -> deserialize round-trips every array and texture."""
     raw = O.duck_pt_bytes()
