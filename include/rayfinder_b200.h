@@ -270,9 +270,9 @@ rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refi
 rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t persistent_kernel, int32_t variant, int32_t block_threads);
 /* Tail policy of the traversal launches (results never depend on it).  Once a launch's ray queue is dry, a warp left
  * with <= evict_max rays keeps them for four more loop rounds (most of them are short and end there), then writes the
- * traversal state of the rest to a device buffer and exits; a small follow-up launch packs
- * those stragglers densely and finishes them with node prefetching, so the SMs they pinned are free for the other
- * tile sets' kernels.  0 = off (every ray ends on the lane it started on), -1 = automatic (the default: 8 when this
+ * traversal state of the rest to a device buffer and exits; a follow-up launch gives each of those rays a whole warp
+ * (32 consecutive nodes loaded and slab-tested per memory round trip, csrc/straggler.cuh), which walks the long ones
+ * ~2.5x faster than a lone lane can.  0 = off (every ray ends on the lane it started on), -1 = automatic (the default: 8 when this
  * GPU owns at most ~0.6 M pixels — launches that are mostly tail — else off), up to 32. */
 rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
 
