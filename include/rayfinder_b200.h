@@ -244,15 +244,23 @@ uint32_t  rf_renderer_accumulated_sample_count(const rf_renderer* r);
  * bit-identical to a single-GPU frame.  Resets the accumulation. */
 rf_status rf_renderer_set_tile_partition(rf_renderer* r, uint32_t rank, uint32_t world);
 
-/* The exchange fused into the accumulation kernel (one process per GPU, same node).  The root rank exports its HDR buffer
- * (64-byte CUDA IPC handle); every other rank maps it, and from then on its accumulation kernel also stores each owned
- * pixel's accumulated value into the root's buffer over NVLink peer memory.  A pixel has exactly one owner, so after all
- * ranks have finished the frame (any stream-ordered barrier, e.g. a 4-byte all-reduce) the root's buffer holds the full
- * frame, bit-identical to the single-GPU one, without moving W x H x 16 bytes through a reduction.  The root must not
- * restart its own accumulation (which clears the buffer) while other ranks are still writing a frame: keep the ranks in
- * step with the barrier, as rayfinder_b200/distributed.py does.  NULL detaches. */
+/* The exchange fused into the accumulation kernel (one process per GPU, same node).  The root rank allocates and exports an
+ * exchange buffer of TWO full frames (64-byte CUDA IPC handle); every other rank maps it, and from then on the accumulation
+ * kernel of every rank — the root included — also stores each owned pixel's accumulated value into half (frame & 1) of that
+ * buffer, over NVLink peer memory on the other ranks.  A pixel has exactly one owner, so after all ranks have finished the
+ * frame (any stream-ordered barrier, e.g. a 4-byte all-reduce) that half holds the full frame, bit-identical to the
+ * single-GPU one, without moving W x H x 16 bytes through a reduction; rf_renderer_read_hdr / _read_display /
+ * rf_renderer_exchange_device_ptr on the root then present it.  The double buffer is what makes the root's read safe: the
+ * other ranks may already be storing frame N + 1 (into the other half) while the root still reads frame N, and they come
+ * back to this half only after the barrier of frame N + 1, which the root enters — in stream order — after its read.
+ * Contract: every rank is created with the same maxFramebufferSize, calls rf_renderer_render the same number of times
+ * with the same parameters, and runs the barrier after every frame on the rendering stream, as
+ * rayfinder_b200/distributed.py does.  The local HDR buffer (rf_renderer_hdr_device_ptr) is never written by another rank.
+ * NULL detaches. */
 rf_status rf_renderer_hdr_ipc_handle(rf_renderer* r, void* out_handle_64_bytes);
 rf_status rf_renderer_set_hdr_peer(rf_renderer* r, const void* handle_64_bytes);
+/* Root of an exchange: the half of the exchange buffer that holds the last complete frame (float4[W*H]); else NULL. */
+void*     rf_renderer_exchange_device_ptr(rf_renderer* r);
 
 rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out);
 rf_status rf_renderer_reset_stats(rf_renderer* r);
@@ -275,6 +283,13 @@ rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t p
  * ~2.5x faster than a lone lane can.  0 = off (every ray ends on the lane it started on), -1 = automatic (the default: 8 when this
  * GPU owns at most ~0.6 M pixels — launches that are mostly tail — else off), up to 32. */
 rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
+/* Named scheduling / debugging knobs (results never depend on them; unknown names are an error):
+ *   "shade_wait"   persistent kernel: 0.5 us naps its shading warp takes to let a batch of 32 hits fill (default 16)
+ *   "evict_delay"  loop rounds a warp keeps its last rays before handing them to the tail launch (default 4)
+ *   "trace_stack"  force at least this many traversal-stack entries (<= 32; 0 = what the scene needs, the default)
+ *   "stage_debug"  1: print the per-launch spans of every stage-timed frame to stderr
+ *   "mega_debug"   1: print the persistent kernel's control block after every frame (synchronises) */
+rf_status rf_renderer_set_option(rf_renderer* r, const char* name, int64_t value);
 
 /* ---- the deferred renderer's lighting + resolve passes as a second integrator -------
  * pt/deferred_renderer_lighting_pass.wgsl:96-186 and pt/deferred_renderer_resolve_pass.wgsl:34-53, i.e. the

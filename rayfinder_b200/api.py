@@ -373,6 +373,13 @@ class ReferencePathTracer:
     def hdr_device_ptr(self) -> int:
         return lib().rf_renderer_hdr_device_ptr(self._handle) or 0
 
+    def exchange_device_ptr(self) -> int:
+        """Root of a peer-memory exchange: device pointer of the last complete exchanged frame (0 otherwise)."""
+        return lib().rf_renderer_exchange_device_ptr(self._handle) or 0
+
+    def set_option(self, name: str, value: int) -> None:
+        check(lib().rf_renderer_set_option(self._handle, name.encode(), int(value)))
+
     def set_stream(self, cuda_stream: int) -> None:
         check(lib().rf_renderer_set_stream(self._handle, C.c_void_p(cuda_stream)))
 

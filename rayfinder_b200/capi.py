@@ -118,6 +118,8 @@ SIGNATURES = {
     "rf_renderer_set_tail_policy": (C.c_int32, [_P, C.c_int32]),
     "rf_renderer_hdr_ipc_handle": (C.c_int32, [_P, _P]),
     "rf_renderer_set_hdr_peer": (C.c_int32, [_P, _P]),
+    "rf_renderer_exchange_device_ptr": (_P, [_P]),
+    "rf_renderer_set_option": (C.c_int32, [_P, C.c_char_p, C.c_int64]),
     "rf_renderer_render_deferred_lighting": (C.c_int32, [_P, C.POINTER(DeferredLightingParams), _P, _P, _P]),
     "rf_renderer_read_deferred": (C.c_int32, [_P, _P, _P, _P]),
     "rf_traversal_scene_create": (C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(_P)]),

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <string>
 #include <vector>
 
 using namespace rfb200;
@@ -109,9 +110,13 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
                 return setError(RF_ERROR_INVALID_ARGUMENT, "BVH interior node %llu has child indices out of order.", (unsigned long long)i);
         }
     }
-    // Depth check (explicit stack; the tree is a proper pre-order tree after the checks above).
+    // Depth check (explicit stack).  Every node must have exactly one parent: a node reached twice means the records
+    // describe a DAG, whose root-to-leaf paths can be exponentially many — rejected at the second visit, which keeps
+    // this walk O(numNodes).
     std::vector<std::pair<std::uint32_t, std::uint32_t>> stack;
+    std::vector<std::uint8_t>                            reached(numNodes, 0);
     stack.emplace_back(0u, 0u);
+    reached[0] = 1;
     std::uint32_t maxPending = 0;
     while (!stack.empty())
     {
@@ -122,8 +127,14 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
         {
             // descending into one child leaves the other pending on the traversal stack
             maxPending = std::max(maxPending, pending + 1);
-            stack.emplace_back(idx + 1, pending + 1);
-            stack.emplace_back(n.second_child_offset, pending + 1);
+            if (maxPending > static_cast<std::uint32_t>(RF_STACK_SIZE)) break;
+            for (const std::uint32_t child : {idx + 1u, n.second_child_offset})
+            {
+                if (reached[child])
+                    return setError(RF_ERROR_INVALID_ARGUMENT, "BVH node %u has more than one parent.", child);
+                reached[child] = 1;
+                stack.emplace_back(child, pending + 1);
+            }
         }
     }
     if (maxPending > static_cast<std::uint32_t>(RF_STACK_SIZE))
@@ -132,15 +143,8 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
     return RF_OK;
 }
 
-// Scheduling knobs of the persistent traversal loop; RF_TRI_MIN / RF_REFILL_MIN override for sweeps.
-TraceTuning defaultTuning()
-{
-    TraceTuning t{4u, 4u, 16u};
-    if (const char* e = std::getenv("RF_MEGA_SHADE_WAIT")) t.shadeWait = static_cast<std::uint32_t>(std::max(0, std::atoi(e)));
-    if (const char* e = std::getenv("RF_TRI_MIN")) t.triMin = static_cast<std::uint32_t>(std::max(1, std::atoi(e)));
-    if (const char* e = std::getenv("RF_REFILL_MIN")) t.refillMin = static_cast<std::uint32_t>(std::max(1, std::atoi(e)));
-    return t;
-}
+// Scheduling knobs of the persistent traversal loop (rf_renderer_set_tuning / rf_renderer_set_option change them).
+TraceTuning defaultTuning() { return TraceTuning{4u, 4u, 16u}; }
 
 bool sameParams(const rf_render_parameters& a, const rf_render_parameters& b)
 {
@@ -287,8 +291,21 @@ struct rf_renderer
         std::uint32_t               width = 0, height = 0;
         float                       exposure = 1.0f;
     } deferred;
-    float4*       peerImage = nullptr;  // the root rank's HDR buffer mapped through CUDA IPC (rf_renderer_set_hdr_peer)
-    bool          exportedRoot = false; // this renderer's HDR buffer is the target of the other ranks' stores
+    // Multi-GPU exchange over peer memory (rf_renderer_hdr_ipc_handle / rf_renderer_set_hdr_peer).  The root owns
+    // `exchange`: TWO full frames.  Frame N of every rank (the root included) stores its owned pixels into half N & 1, so
+    // the root can read frame N while the other ranks already write frame N + 1 into the other half; they reach half
+    // N & 1 again only after the frame barrier of N + 1, which the root enters after its read (stream order).
+    DeviceBuffer<float4> exchange;
+    float4*       peerImage = nullptr;  // both halves: the root's own `exchange.ptr`, or its mapping through CUDA IPC on the other ranks
+    bool          exportedRoot = false; // this renderer owns the exchange buffer
+    std::uint32_t exchangeEpoch = 0;    // frames accumulated since the exchange was set up (same on every rank)
+    std::uint64_t exchangeStride() const { return static_cast<std::uint64_t>(maxW) * maxH; }
+    float4*       exchangeTarget() const { return peerImage ? peerImage + (exchangeEpoch & 1u) * exchangeStride() : nullptr; }
+    // what read_hdr / read_display show: the last complete exchanged frame on the root of an exchange, else the local image
+    const float4* presentedImage() const
+    {
+        return exportedRoot && exchangeEpoch > 0 ? exchange.ptr + ((exchangeEpoch - 1u) & 1u) * exchangeStride() : image.ptr;
+    }
     std::uint64_t kernelLaunches = 0;   // kernels launched by render() since the last reset_stats
     int         numSubFrames = 2;       // in effect (updateTiles)
     int         requestedSubFrames = 0; // 0: automatic
@@ -336,7 +353,7 @@ struct rf_renderer
             if (sf.done) cudaEventDestroy(sf.done);
         }
         if (forkEvent) cudaEventDestroy(forkEvent);
-        if (peerImage) cudaIpcCloseMemHandle(peerImage);
+        if (peerImage && !exportedRoot) cudaIpcCloseMemHandle(peerImage);
     }
 
     void drainTimings(bool wait)
@@ -376,7 +393,7 @@ struct rf_renderer
                 }
                 msTrace += span(e, e + 1);
                 msOther += span(e + 1, e + 2);
-                if (std::getenv("RF_DEBUG_STAGES"))
+                if (stageDebug)
                 {
                     // per-launch spans of one frame: raygen, then (trace, shade) per bounce, last trace, accumulate
                     std::fprintf(stderr, "[stages] total %.3f:", ms);
@@ -392,11 +409,14 @@ struct rf_renderer
 
     rf_status applyParams(const rf_render_parameters& p)
     {
+        // the sky state first: a rejected sky must leave the renderer as it was (params, sky state and accumulation)
+        rf_sky_state    newSky{};
+        const rf_status st = rf_sky_state_new(&p.sky, &newSky);
+        if (st != RF_OK) return st;
+        skyState = newSky;
         if (p.framebuffer_width != params.framebuffer_width || p.framebuffer_height != params.framebuffer_height) tilesDirty = true;
         params = p;
         accumulated = 0; // reset the temporal accumulation (reference_path_tracer.cpp:561)
-        const rf_status st = rf_sky_state_new(&p.sky, &skyState);
-        if (st != RF_OK) return st;
         // Sampling tables for every n = frameCount % numSamplesPerPixel.
         const std::uint32_t spp = p.sampling_params.num_samples_per_pixel;
         if (spp != lutRows)
@@ -471,12 +491,11 @@ struct rf_renderer
     // paths per GPU (the 1080p frame on 1-2 GPUs) two tile sets on two streams and no hand-over are fastest; below
     // that (a 1080p frame split over 4-8 GPUs) a launch is mostly tail and one tile set with the hand-over wins.
     std::uint32_t stackEntries = RF_STACK_SIZE; // deepest traversal stack the scene can produce (validateBvh)
-    // RF_TRACE_STACK=32 forces the reference-sized stack (A/B runs)
-    std::uint32_t traceStackEntries() const
-    {
-        static const int forced = std::getenv("RF_TRACE_STACK") ? std::atoi(std::getenv("RF_TRACE_STACK")) : 0;
-        return forced > 0 ? std::max(static_cast<std::uint32_t>(forced), stackEntries) : stackEntries;
-    }
+    // option "trace_stack" = 32 forces the reference-sized stack (A/B runs)
+    std::uint32_t forcedStackEntries = 0;
+    std::uint32_t traceStackEntries() const { return std::max(forcedStackEntries, stackEntries); }
+    std::uint32_t evictDelay = 4; // rounds a warp keeps its last rays before handing them over (measured: 4 lets the many short ones end in place)
+    bool          stageDebug = false, megaDebug = false;
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
@@ -586,8 +605,6 @@ extern "C" rf_status rf_renderer_create(
         if (i > 0) RF_CUDA(cudaStreamCreateWithFlags(&r->sub[i].stream, cudaStreamNonBlocking));
         RF_CUDA(cudaEventCreateWithFlags(&r->sub[i].done, cudaEventDisableTiming));
     }
-    if (const char* e = std::getenv("RF_MEGAKERNEL")) r->megakernel = std::atoi(e) != 0;
-    if (const char* e = std::getenv("RF_SUBFRAMES")) r->requestedSubFrames = std::min(std::max(std::atoi(e), 0), static_cast<int>(rf_renderer::MAX_SUBFRAMES));
 
     st = r->applyParams(desc->render_params);
     if (st != RF_OK) return st;
@@ -677,13 +694,14 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     RF_CUDA(cudaEventRecord(t.begin, s));
     const std::uint64_t numPixels = static_cast<std::uint64_t>(fp.width) * fp.height;
     const bool restart = r->accumulated == 0;
-    if (restart && !(r->exportedRoot && r->world > 1))
+    if (restart)
     {
         // fsMain:45-47: imageBuffer[idx] = vec3(0f) on the first sample; k_accumulate does that for the owned pixels, this
-        // clears the others (what a sum-reduce over ranks needs).  The root of a peer-memory exchange must NOT clear them:
-        // they belong to the other ranks, which overwrite them every frame and may already be writing.
+        // clears the others (what a sum-reduce over ranks needs).  The local image is never written by another rank (the
+        // peer-memory exchange has its own double-buffered target), so the clear cannot race with anything.
         RF_CUDA(cudaMemsetAsync(r->image.ptr, 0, numPixels * sizeof(float4), s));
     }
+    float4* const exchangeTarget = r->exchangeTarget();
     RF_CUDA(cudaEventRecord(r->forkEvent, s));
 
     const int gridLight = r->gridFor(8);
@@ -708,9 +726,9 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             k_mega_init<<<1, 1, 0, ss>>>(sf.control.ptr, &ctr[0]);
             launchMega(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], sf.meta.ptr, r->radiance.ptr, sf.control.ptr, sf.ready.ptr,
                        sf.log2Cap, r->stats.ptr);
-            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, r->peerImage, restart);
+            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, exchangeTarget, restart);
             r->kernelLaunches += 4;
-            if (std::getenv("RF_DEBUG_MEGA"))
+            if (r->megaDebug)
             {
                 MegaControl   c{};
                 std::uint32_t n = 0;
@@ -732,8 +750,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         const std::uint32_t evictMax = staged ? 0u : r->effectiveEvictMax();
         std::uint32_t* const stragglerCounts = ctr + 2u * fp.numBounces + 2u;
         std::uint32_t* const stragglerCursors = ctr + 3u * fp.numBounces + 3u;
-        // rounds a warp keeps its last rays before handing them over (measured: 4 lets the many short ones end in place)
-        static const std::uint32_t evictDelay = std::getenv("RF_EVICT_DELAY") ? static_cast<std::uint32_t>(std::atoi(std::getenv("RF_EVICT_DELAY"))) : 4u;
+        const std::uint32_t evictDelay = r->evictDelay;
         const auto           stragglersOf = [&](std::uint32_t k) { return StragglerBuffer{sf.stragglers.ptr, &stragglerCounts[k], r->stragglerCapacity(), evictMax, evictDelay}; };
         const auto           finishStragglers = [&](std::uint32_t k, const PathQueue& closestQueue, const PathQueue& shadowQueue) {
             if (evictMax == 0u) return;
@@ -761,7 +778,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             finishStragglers(bounce, sf.queues[outQ], sf.queues[outQ]);
         }
         RF_CUDA(stageMark());
-        k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, r->peerImage, restart);
+        k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, exchangeTarget, restart);
         // raygen + (numBounces + 1) traversal launches (+ their straggler follow-ups) + numBounces shades + accumulate
         r->kernelLaunches += 2ull + (fp.numBounces + 1ull) * (evictMax != 0u ? 2ull : 1ull) + fp.numBounces;
         RF_CUDA(stageMark());
@@ -776,6 +793,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     r->pending.push_back(std::move(t));
     r->frames++;
     r->accumulated = std::min(r->accumulated + 1, spp); // reference_path_tracer.cpp:590-591
+    if (r->peerImage) ++r->exchangeEpoch;
 
     return RF_OK;
 }
@@ -942,7 +960,7 @@ extern "C" rf_status rf_renderer_read_hdr(rf_renderer* r, float* dst, std::uint6
     const std::uint64_t need = static_cast<std::uint64_t>(r->params.framebuffer_width) * r->params.framebuffer_height * 4;
     if (numFloats < need) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_hdr: need %llu floats, got %llu", (unsigned long long)need, (unsigned long long)numFloats);
     RF_CUDA(cudaSetDevice(r->device));
-    RF_CUDA(cudaMemcpyAsync(dst, r->image.ptr, need * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RF_CUDA(cudaMemcpyAsync(dst, r->presentedImage(), need * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
     RF_CUDA(cudaStreamSynchronize(r->stream));
     if (accumulated) *accumulated = r->accumulated;
     return RF_OK;
@@ -955,7 +973,7 @@ extern "C" rf_status rf_renderer_read_display(rf_renderer* r, std::uint32_t* dst
     if (numPixels < need) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_read_display: need %llu pixels", (unsigned long long)need);
     RF_CUDA(cudaSetDevice(r->device));
     const float acc = static_cast<float>(std::max(r->accumulated, 1u));
-    k_display<<<r->gridFor(8), BLOCK_THREADS, 0, r->stream>>>(static_cast<std::uint32_t>(need), r->image.ptr, acc, r->params.exposure, r->display.ptr);
+    k_display<<<r->gridFor(8), BLOCK_THREADS, 0, r->stream>>>(static_cast<std::uint32_t>(need), r->presentedImage(), acc, r->params.exposure, r->display.ptr);
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaMemcpyAsync(dst, r->display.ptr, need * 4, cudaMemcpyDeviceToHost, r->stream));
     RF_CUDA(cudaStreamSynchronize(r->stream));
@@ -1081,10 +1099,19 @@ extern "C" rf_status rf_renderer_hdr_ipc_handle(rf_renderer* r, void* outHandle6
 {
     if (!r || !outHandle64) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_hdr_ipc_handle: null argument");
     RF_CUDA(cudaSetDevice(r->device));
+    RF_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->peerImage && !r->exportedRoot) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_hdr_ipc_handle: this renderer is attached to another root");
+    if (!r->exchange.ptr)
+    {
+        RF_CUDA(r->exchange.allocate(2 * r->exchangeStride()));
+        RF_CUDA(cudaMemset(r->exchange.ptr, 0, 2 * r->exchangeStride() * sizeof(float4)));
+    }
     cudaIpcMemHandle_t h;
-    RF_CUDA(cudaIpcGetMemHandle(&h, r->image.ptr));
+    RF_CUDA(cudaIpcGetMemHandle(&h, r->exchange.ptr));
     std::memcpy(outHandle64, &h, sizeof(h));
     r->exportedRoot = true;
+    r->peerImage = r->exchange.ptr; // the root stores its own pixels there too
+    r->exchangeEpoch = 0;
     return RF_OK;
 }
 
@@ -1095,16 +1122,15 @@ extern "C" rf_status rf_renderer_set_hdr_peer(rf_renderer* r, const void* handle
     RF_CUDA(cudaStreamSynchronize(r->stream));
     for (auto& sf : r->sub)
         if (sf.stream) RF_CUDA(cudaStreamSynchronize(sf.stream));
-    if (r->peerImage)
-    {
-        RF_CUDA(cudaIpcCloseMemHandle(r->peerImage));
-        r->peerImage = nullptr;
-    }
+    if (r->peerImage && !r->exportedRoot) RF_CUDA(cudaIpcCloseMemHandle(r->peerImage));
+    r->peerImage = nullptr;
+    r->exchangeEpoch = 0;
     if (!handle64)
     {
-        r->exportedRoot = false;
+        r->exportedRoot = false; // the root keeps its buffer until the renderer is destroyed (peers may still unmap it)
         return RF_OK;
     }
+    if (r->exportedRoot) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_hdr_peer: this renderer is the root of an exchange");
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle64, sizeof(h));
     void* mapped = nullptr;
@@ -1113,11 +1139,31 @@ extern "C" rf_status rf_renderer_set_hdr_peer(rf_renderer* r, const void* handle
     return RF_OK;
 }
 
+extern "C" void* rf_renderer_exchange_device_ptr(rf_renderer* r)
+{
+    return r && r->exportedRoot ? const_cast<float4*>(r->presentedImage()) : nullptr;
+}
+
 extern "C" rf_status rf_renderer_set_tail_policy(rf_renderer* r, std::int32_t evictMax)
 {
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tail_policy: null renderer");
     if (evictMax > 32) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_tail_policy: value out of range");
     r->evictMax = evictMax < 0 ? -1 : evictMax;
+    return RF_OK;
+}
+
+// Named scheduling / debugging knobs that used to be environment variables; results never depend on them.
+extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, std::int64_t value)
+{
+    if (!r || !name) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: null argument");
+    const std::string key(name);
+    if (value < 0 || value > (1ll << 30)) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: value of '%s' out of range", name);
+    if (key == "shade_wait") r->tuning.shadeWait = static_cast<std::uint32_t>(value);
+    else if (key == "evict_delay") r->evictDelay = static_cast<std::uint32_t>(value);
+    else if (key == "trace_stack") r->forcedStackEntries = static_cast<std::uint32_t>(std::min<std::int64_t>(value, RF_STACK_SIZE));
+    else if (key == "stage_debug") r->stageDebug = value != 0;
+    else if (key == "mega_debug") r->megaDebug = value != 0;
+    else return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: unknown option '%s'", name);
     return RF_OK;
 }
 

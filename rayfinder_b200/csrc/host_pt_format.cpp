@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <new>
 #include <regex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -134,10 +136,18 @@ rf_status parse(const std::uint8_t* data, std::uint64_t size, rf_pt_file& f)
                 r.read(&t.width, 4);
                 r.read(&t.height, 4);
                 const std::uint64_t n = r.u64();
-                if (!r.ok || static_cast<std::uint64_t>(r.end - r.cur) < n * 4)
+                if (!r.ok || n > static_cast<std::uint64_t>(r.end - r.cur) / 4) // (no n * 4: it wraps for n >= 2^62)
                 {
                     r.ok = false;
                     break;
+                }
+                // Every consumer reads width * height texels (Texture::pixels() is exactly that in the reference,
+                // common/texture.hpp; reference_path_tracer.cpp:229-269 uploads pixels().size()): a file that says otherwise
+                // is malformed, not a short read.
+                if (n != static_cast<std::uint64_t>(t.width) * t.height)
+                {
+                    return setError(RF_ERROR_FORMAT, "Invalid PtFormat file: texture %llu has %llu pixels for %ux%u.",
+                                    (unsigned long long)(&t - f.textures.data()), (unsigned long long)n, t.width, t.height);
                 }
                 t.pixels.resize(n);
                 r.read(t.pixels.data(), n * 4);
@@ -184,13 +194,38 @@ void serializeTo(const rf_pt_file& f, std::uint8_t* dst)
         put(t.pixels.data(), 4 * n);
     }
 }
+
+// No C++ exception may cross the extern "C" boundary (std::terminate): allocation failures of the containers
+// become a status code.
+template<class F>
+rf_status guarded(const char* what, F&& body)
+{
+    try
+    {
+        return body();
+    }
+    catch (const std::bad_alloc&)
+    {
+        return setError(RF_ERROR_IO, "%s: out of memory", what);
+    }
+    catch (const std::length_error&)
+    {
+        return setError(RF_ERROR_INVALID_ARGUMENT, "%s: size out of range", what);
+    }
+    catch (const std::exception& e)
+    {
+        return setError(RF_ERROR_IO, "%s: %s", what, e.what());
+    }
+}
 } // namespace
 
 extern "C" rf_status rf_pt_create(rf_pt_file** out)
 {
     if (!out) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_create: null argument");
-    *out = new rf_pt_file();
-    return RF_OK;
+    return guarded("rf_pt_create", [&]() -> rf_status {
+        *out = new rf_pt_file();
+        return RF_OK;
+    });
 }
 
 extern "C" void rf_pt_destroy(rf_pt_file* f) { delete f; }
@@ -198,11 +233,13 @@ extern "C" void rf_pt_destroy(rf_pt_file* f) { delete f; }
 extern "C" rf_status rf_pt_load_memory(const void* data, std::uint64_t size, rf_pt_file** out)
 {
     if (!data || !out) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_load_memory: null argument");
-    auto            f = std::make_unique<rf_pt_file>();
-    const rf_status st = parse(static_cast<const std::uint8_t*>(data), size, *f);
-    if (st != RF_OK) return st;
-    *out = f.release();
-    return RF_OK;
+    return guarded("rf_pt_load_memory", [&]() -> rf_status {
+        auto            f = std::make_unique<rf_pt_file>();
+        const rf_status st = parse(static_cast<const std::uint8_t*>(data), size, *f);
+        if (st != RF_OK) return st;
+        *out = f.release();
+        return RF_OK;
+    });
 }
 
 extern "C" rf_status rf_pt_load(const char* path, rf_pt_file** out)
@@ -213,14 +250,25 @@ extern "C" rf_status rf_pt_load(const char* path, rf_pt_file** out)
     {
         return setError(RF_ERROR_IO, "Failed to open file: %s", path); // common/file_stream.cpp:13-16
     }
-    std::fseek(fp, 0, SEEK_END);
-    const long size = std::ftell(fp);
-    std::fseek(fp, 0, SEEK_SET);
-    std::vector<std::uint8_t> buf(size > 0 ? static_cast<std::size_t>(size) : 0);
-    const std::size_t         got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), fp);
-    std::fclose(fp);
-    if (got != buf.size()) return setError(RF_ERROR_IO, "Failed to read file: %s", path);
-    return rf_pt_load_memory(buf.data(), buf.size(), out);
+    return guarded("rf_pt_load", [&]() -> rf_status {
+        std::fseek(fp, 0, SEEK_END);
+        const long size = std::ftell(fp);
+        std::fseek(fp, 0, SEEK_SET);
+        std::vector<std::uint8_t> buf;
+        try
+        {
+            buf.resize(size > 0 ? static_cast<std::size_t>(size) : 0);
+        }
+        catch (...)
+        {
+            std::fclose(fp);
+            throw;
+        }
+        const std::size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), fp);
+        std::fclose(fp);
+        if (got != buf.size()) return setError(RF_ERROR_IO, "Failed to read file: %s", path);
+        return rf_pt_load_memory(buf.data(), buf.size(), out);
+    });
 }
 
 extern "C" rf_status rf_pt_save_memory(const rf_pt_file* f, void* dst, std::uint64_t capacity, std::uint64_t* size)
@@ -236,14 +284,16 @@ extern "C" rf_status rf_pt_save_memory(const rf_pt_file* f, void* dst, std::uint
 extern "C" rf_status rf_pt_save(const rf_pt_file* f, const char* path)
 {
     if (!f || !path) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_save: null argument");
-    std::vector<std::uint8_t> buf(serializedSize(*f));
-    serializeTo(*f, buf.data());
-    std::FILE* fp = std::fopen(path, "wb");
-    if (!fp) return setError(RF_ERROR_IO, "Failed to open file: %s", path);
-    const std::size_t put = std::fwrite(buf.data(), 1, buf.size(), fp);
-    std::fclose(fp);
-    if (put != buf.size()) return setError(RF_ERROR_IO, "Failed to write file: %s", path);
-    return RF_OK;
+    return guarded("rf_pt_save", [&]() -> rf_status {
+        std::vector<std::uint8_t> buf(serializedSize(*f));
+        serializeTo(*f, buf.data());
+        std::FILE* fp = std::fopen(path, "wb");
+        if (!fp) return setError(RF_ERROR_IO, "Failed to open file: %s", path);
+        const std::size_t put = std::fwrite(buf.data(), 1, buf.size(), fp);
+        std::fclose(fp);
+        if (put != buf.size()) return setError(RF_ERROR_IO, "Failed to write file: %s", path);
+        return RF_OK;
+    });
 }
 
 extern "C" rf_status rf_pt_array(const rf_pt_file* f, int32_t which, const void** data, std::uint64_t* count, std::uint64_t* elem_size)
@@ -258,9 +308,12 @@ extern "C" rf_status rf_pt_array(const rf_pt_file* f, int32_t which, const void*
 extern "C" rf_status rf_pt_set_array(rf_pt_file* f, int32_t which, const void* data, std::uint64_t count)
 {
     if (!f || which < 0 || which >= RF_PT_NUM_ARRAYS || (!data && count)) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_set_array: bad argument");
-    const auto* p = static_cast<const std::uint8_t*>(data);
-    f->arrays[which].assign(p, p + count * ELEM_SIZE[which]);
-    return RF_OK;
+    if (count > (~0ull >> 1) / ELEM_SIZE[which]) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_set_array: count out of range");
+    return guarded("rf_pt_set_array", [&]() -> rf_status {
+        const auto* p = static_cast<const std::uint8_t*>(data);
+        f->arrays[which].assign(p, p + count * ELEM_SIZE[which]);
+        return RF_OK;
+    });
 }
 
 extern "C" std::uint64_t rf_pt_num_textures(const rf_pt_file* f) { return f ? f->textures.size() : 0; }
@@ -276,11 +329,13 @@ extern "C" rf_status rf_pt_texture(const rf_pt_file* f, std::uint64_t idx, rf_te
 extern "C" rf_status rf_pt_add_texture(rf_pt_file* f, const std::uint32_t* pixels, std::uint32_t width, std::uint32_t height)
 {
     if (!f || !pixels) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_add_texture: null argument");
-    TextureData t;
-    t.width = width, t.height = height;
-    t.pixels.assign(pixels, pixels + static_cast<std::uint64_t>(width) * height);
-    f->textures.push_back(std::move(t));
-    return RF_OK;
+    return guarded("rf_pt_add_texture", [&]() -> rf_status {
+        TextureData t;
+        t.width = width, t.height = height;
+        t.pixels.assign(pixels, pixels + static_cast<std::uint64_t>(width) * height);
+        f->textures.push_back(std::move(t));
+        return RF_OK;
+    });
 }
 
 extern "C" rf_status rf_pt_scene(const rf_pt_file* f, rf_scene* out, rf_texture* textures)

@@ -91,3 +91,16 @@ def test_renderer_argument_validation(duck_pt):
     with pytest.raises(rf.RayfinderError) as e:
         rf.TraversalScene(bad, O.triangles9(duck_pt))
     assert "out of range" in str(e.value)
+    # a DAG (every interior node i points at i + 1 and i + 2): structurally "ordered", but a node with two parents would
+    # make the depth walk enumerate Fibonacci-many paths — it must be rejected at once
+    import time
+    n = 60  # (the longest descent stays below the 32-entry stack limit, so that check does not fire first)
+    dag = np.zeros(n, dtype=rf.BVH_NODE_DTYPE)
+    dag["aabb_max"] = 1.0
+    dag["second_child_offset"] = np.arange(n) + 2
+    dag["triangle_count"][n - 2:] = 1
+    dag["split_axis"][n - 2:] = 0xFFFFFFFF
+    t0 = time.perf_counter()
+    with pytest.raises(rf.RayfinderError) as e:
+        rf.TraversalScene(dag, O.triangles9(duck_pt))
+    assert "more than one parent" in str(e.value) and time.perf_counter() - t0 < 1.0

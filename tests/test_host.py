@@ -186,6 +186,26 @@ def test_pt_truncated_and_missing_file(tmp_path):
     assert str(e.value) == f"Failed to open file: {tmp_path / 'nope.pt'}"  # common/file_stream.cpp:13-16
 
 
+def test_pt_texture_pixel_count_must_match_its_size():
+    """A texture whose numPixels differs from width x height would make every consumer (which reads width x height
+    texels) run past the pixel array: rejected as malformed; a count whose byte size wraps 64 bits is a short read."""
+    raw = bytearray(O.duck_pt_bytes())
+    pt = rf.PtFormat.loads(bytes(raw))
+    tex = pt.base_color_textures[0]
+    header = len(raw) - tex.size * 4 - 16  # [u32 width][u32 height][u64 numPixels] of the only texture
+    assert np.frombuffer(raw[header:header + 8], dtype="<u4").tolist() == [tex.shape[1], tex.shape[0]]
+    grown = bytearray(raw)
+    grown[header:header + 4] = np.uint32(tex.shape[1] * 2).tobytes()  # width doubled, pixel count unchanged
+    with pytest.raises(rf.RayfinderError) as e:
+        rf.PtFormat.loads(bytes(grown))
+    assert e.value.status == capi.RF_ERROR_FORMAT and "pixels for" in str(e.value)
+    wrapped = bytearray(raw)
+    wrapped[header + 8:header + 16] = np.uint64(1 << 62).tobytes()  # n * 4 == 0 (mod 2^64)
+    with pytest.raises(rf.RayfinderError) as e:
+        rf.PtFormat.loads(bytes(wrapped))
+    assert e.value.status == capi.RF_ERROR_IO
+
+
 def test_reorder_attributes():
     idx = np.array([2, 0, 1], dtype=np.uint64)
     assert rf.reorder_attributes(np.array([10, 20, 30]), idx).tolist() == [20, 30, 10]  # bvh.hpp:36-46

@@ -29,18 +29,21 @@ def _worker(rank: int, world: int, port: int, out_path: str):
         pt = rf.PtFormat.loads(O.duck_pt_bytes())
         cam = rf.camera_to_array(rf.bvh_visualizer_camera(pt.bvh_nodes, W, H))
         orc = O.OracleRenderer(pt, W, H, cam, rf.sky_state(rf.Sky()), SPP, BOUNCES, rank=rank, world=world, threads=1)
-        for _ in range(SPP):
-            orc.render()
-        owner = rfd.tile_owner(W, H, world)
-        assert np.all(orc.image[owner != rank] == 0.0)  # non-owned pixels are exactly zero
-        assert orc.stats()["paths"] == SPP * rfd.owned_pixel_count(W, H, rank, world)
-        t = torch.from_numpy(orc.image)
+        t = torch.from_numpy(orc.image)  # the rank's accumulation buffer (the oracle adds into it in place)
         exchange = rfd.HdrExchange(None, W, H, mode="auto", tensor=t)  # host tensor: the reduce, whatever mode is asked for
         assert exchange.mode == "nccl" and exchange.world == world and exchange.rank == rank
-        assert exchange() is t
+        owner = rfd.tile_owner(W, H, world)
+        for _ in range(SPP):
+            # progressive render: the exchange runs after EVERY frame and must not feed back into the accumulation
+            orc.render()
+            reduced = exchange()
+            assert reduced is not t
+            assert np.all(orc.image[owner != rank] == 0.0)  # non-owned pixels stay exactly zero on every rank, root included
+        assert orc.stats()["paths"] == SPP * rfd.owned_pixel_count(W, H, rank, world)
+        t = reduced
         exchange.close()
         with pytest.raises(ValueError):
-            rfd.HdrExchange(None, W, H, mode="p2p", tensor=t)
+            rfd.HdrExchange(None, W, H, mode="p2p", tensor=torch.from_numpy(orc.image))
         counters = torch.from_numpy(orc.counters.astype(np.int64))
         dist.all_reduce(counters)
         if rank == 0:
