@@ -28,9 +28,10 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "Mrays/s (Sponza 1080p, 8 bounces)"
+DATA_NOTE = "Sponza.pt baked from the reference's assets/Sponza.glb (deterministic asset, not synthetic)"
 UNIT = "Mrays/s"
-WIDTH, HEIGHT, BOUNCES = 1920, 1080, 8
-KERNELS_PER_STEP = 3 + 2 * BOUNCES  # raygen + trace + (shade, trace) per bounce + accumulate
+BOUNCES = 8
+CONFIGS = {"1080p": (1920, 1080), "4k": (3840, 2160)}
 
 
 def parse_args():
@@ -39,28 +40,19 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--width", type=int, default=WIDTH)
-    p.add_argument("--height", type=int, default=HEIGHT)
+    p.add_argument("--config", default="1080p", choices=sorted(CONFIGS),
+                   help="1080p = BASELINE.json configs[1] (the metric's configuration); 4k = configs[3] (3840x2160, meant for --gpus 8)")
+    p.add_argument("--width", type=int, default=None)
+    p.add_argument("--height", type=int, default=None)
     p.add_argument("--bounces", type=int, default=BOUNCES)
-    p.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per bounded reference sample")
+    p.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU exchange step (rayfinder_b200/distributed.py)")
+    p.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work per bounded reference sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    return p.parse_args()
-
-
-def load_scene():
-    import rayfinder_b200 as rf
-
-    from rayfinder_b200 import assets as rfa
-
-    if rfa.scene_path("Sponza") is not None:
-        return rfa.load_scene("Sponza"), "Sponza.pt"
-    import _oracle as O  # fixture loader only (no oracle code runs)
-
-    return rf.PtFormat.loads(O.duck_pt_bytes()), "Duck.pt (Sponza.pt not baked on this box)"
-
-
-def workload_name(scene_name, w, h, bounces):
-    return f"{scene_name} {w}x{h}, 1 spp, {bounces} bounces, interior fly-camera default view"
+    args = p.parse_args()
+    cw, ch = CONFIGS[args.config]
+    args.width = args.width or cw
+    args.height = args.height or ch
+    return args
 
 
 # ---- clocks -------------------------------------------------------------------------------------------
@@ -174,88 +166,123 @@ class ClockSampler:
 
 
 # ---- the reference's CPU traversal ------------------------------------------------------------------------
-class CpuTraversal:
-    """bvh-visualizer's pixel loop (bvh-visualizer/main.cpp:60-78) over the benchmark view's primary rays, using the
-    reference's own compiled rayIntersectBvh (oracle/_ref, kind "reference") or, if that library is absent, the
-    oracle port (kind "port"); rows are spread over all host threads."""
+class CpuReference:
+    """The reference's own CPU implementation of the path's hot loop — nlrs::rayIntersectBvh
+    (common/ray_intersection.cpp:138-213), compiled from the reference's sources into oracle/_ref (kind "reference"; the
+    oracle's port when that library is absent, kind "port") — on THE SAME WORKLOAD as the GPU arm: the rays the path tracer
+    traces for this frame (the closest-hit ray of every bounce and the shadow ray of every hit), generated once, untimed,
+    by the oracle's restatement of the WGSL path tracer for every `tile_stride`-th 32x32 tile of the frame.  The reference
+    has no CPU any-hit traversal (shadowRay exists in WGSL only), so shadow rays are traced as closest-hit rays too.
+    Loads the scene with numpy and builds the camera with the reference's createCamera: nothing of rayfinder_b200 is
+    imported or mapped."""
 
-    def __init__(self, pt, width, height):
+    def __init__(self, width, height, bounces, tile_stride=16):
         import _oracle as O
-        import rayfinder_b200 as rf
 
         self.O = O
-        self.nodes = np.ascontiguousarray(pt.bvh_nodes)
-        self.tris = O.triangles9(pt)
-        self.cam = rf.camera_to_array(rf.fly_camera(width, height))
-        self.width, self.height = width, height
+        self.pt = O.NumpyPt.load_scene("Sponza")
+        if self.pt is None:
+            raise SystemExit("bench.py: assets/Sponza.pt[.xz] is missing (bake it with __graft_entry__.build() where the reference is mounted)")
+        self.width, self.height, self.bounces, self.tile_stride = width, height, bounces, tile_stride
+        self.nodes = np.ascontiguousarray(self.pt.bvh_nodes)
+        self.tris = np.ascontiguousarray(self.pt.bvh_position_attributes)
+        self.cam = O.fly_camera_array(width, height)
+        self.sky = O.default_sky_state()
         self.kind = "reference" if O.have_ref() else "port"
         self.cores = O.num_threads()
-        self.t_max = rf.FLT_MAX
+        self.rays, kinds = O.frame_rays(self.pt, width, height, self.cam, self.sky, 1, bounces, tile_stride=tile_stride)
+        self.shadow_fraction = float(kinds.mean()) if kinds.size else 0.0
+        self.t_max = 10000.0  # T_MAX, wgsl:73
 
-    def run_rows(self, rows: int, offset: int = 0):
-        """Trace `rows` image rows taken as 8 evenly spaced bands; returns (rays, seconds)."""
-        bands = 8
-        per = max(1, rows // bands)
-        rays, secs = 0, 0.0
-        fn = self.O.ref_node_counts if self.kind == "reference" else self.O.oracle_node_counts
-        for b in range(bands):
-            r0 = min(self.height - per, (b * self.height) // bands + offset % max(1, self.height // bands - per + 1))
-            _, s = fn(self.nodes, self.tris, self.cam, self.width, self.height, self.t_max, threads=self.cores, rows=(r0, r0 + per))
-            rays += per * self.width
-            secs += s
-        return rays, secs
+    def trace(self, passes: int = 1, threads: int | None = None, limit: int | None = None):
+        """`passes` passes over the ray sample (its first `limit` rays); returns (rays, seconds)."""
+        fn = self.O.ref_intersect if self.kind == "reference" else self.O.oracle_intersect
+        rays = self.rays if limit is None else self.rays[:limit]
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            fn(self.nodes, self.tris, rays, self.t_max, threads=threads or self.cores)
+        return passes * len(rays), time.perf_counter() - t0
 
     def calibrate(self, seconds: float) -> int:
-        """Rows per sample so that one sample is about `seconds` of wall time; more than `height` rows means
-        repeated passes over the frame."""
-        rays, secs = self.run_rows(64)
+        """Passes over the sample so that one bounded sample is about `seconds` of wall time."""
+        n = min(len(self.rays), 200_000)
+        rays, secs = self.trace(1, limit=n)
         rate = rays / max(secs, 1e-9)
-        rows = int(max(8, (rate * seconds) / self.width))
-        if rows >= self.height:
-            return self.height * max(1, rows // self.height)
-        return (rows // 8) * 8
+        return max(1, int(rate * seconds / max(1, len(self.rays))))
 
-    def run_sample(self, rows: int, offset: int = 0):
-        if rows <= self.height:
-            return self.run_rows(rows, offset)
-        rays = secs = 0.0
-        for _ in range(rows // self.height):
-            r, s = self.run_rows(self.height)
-            rays, secs = rays + r, secs + s
-        return rays, secs
+    def primary_rays(self, seconds: float):
+        """bvh-visualizer's own loop (bvh-visualizer/main.cpp:60-78) over the primary rays of the view, as round 1 reported."""
+        fn = self.O.ref_node_counts if self.kind == "reference" else self.O.oracle_node_counts
+        rows, rays, secs = 64, 0, 0.0
+        while secs < seconds:
+            for band in range(8):
+                r0 = min(self.height - rows // 8, (band * self.height) // 8)
+                _, s = fn(self.nodes, self.tris, self.cam, self.width, self.height, 3.4028234663852886e38, threads=self.cores, rows=(r0, r0 + rows // 8))
+                rays, secs = rays + (rows // 8) * self.width, secs + s
+            rows = min(rows * 4, self.height)
+        return rays / secs / 1e6
 
-    def sample_description(self, rows: int) -> str:
-        what = (f"{rows // self.height} full passes over" if rows >= self.height
-                else f"{rows} of {self.height} rows (8 evenly spaced bands) of")
-        return (f"{what} the {self.width}x{self.height} primary rays, bvh-visualizer loop, tmax=FLT_MAX, "
-                f"{self.cores} threads")
+    def full_path_port(self):
+        """The oracle's restatement of the whole WGSL path tracer (kind "port": the reference has no CPU path tracer) on
+        one full frame of the view: (Mrays/s including shading, sample description, exact rays of the frame)."""
+        orc = self.O.OracleRenderer(self.pt, self.width, self.height, self.cam, self.sky, 1, self.bounces)
+        orc.render()
+        st = orc.stats()
+        rays = st["closest_rays"] + st["shadow_rays"]
+        return rays / orc.seconds / 1e6, f"one {self.width}x{self.height} frame, {self.cores} threads", rays
+
+    def sample_description(self, passes: int, threads: int | None = None, limit: int | None = None) -> str:
+        n = len(self.rays) if limit is None else min(limit, len(self.rays))
+        return (f"{passes} pass(es) over {n} rays = the closest-hit + shadow rays ({100 * self.shadow_fraction:.0f}% shadow) of every "
+                f"{self.tile_stride}th 32x32 tile of the {self.width}x{self.height}, {self.bounces}-bounce frame, each through the reference's "
+                f"rayIntersectBvh (closest-hit; the CPU code has no any-hit mode), tmax 10000, {threads or self.cores} thread(s)")
+
+
+def base_config(width, height, bounces, rays_per_step, paths_per_step, l2, pipeline, partition):
+    """The `config` object of both arms: same keys, so the two lines describe the same workload."""
+    return {"workload": f"Sponza.pt {width}x{height}, 1 spp, {bounces} bounces, interior fly-camera default view",
+            "rays_per_step": rays_per_step, "paths_per_step": paths_per_step, "l2": l2, "pipeline": pipeline, "partition": partition}
+
+
+def cpu_baseline_block(cpu: CpuReference, seconds: float) -> dict:
+    passes = cpu.calibrate(seconds)
+    rays, secs = cpu.trace(passes)
+    one_n = min(len(cpu.rays), 100_000)
+    one_rays, one_secs = cpu.trace(1, threads=1, limit=one_n)
+    port_value, port_sample, _ = cpu.full_path_port()
+    return {"value": rays / secs / 1e6, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample_description(passes),
+            "one_core": {"value": one_rays / one_secs / 1e6, "unit": UNIT, "cores": 1, "sample": cpu.sample_description(1, 1, one_n),
+                         "note": "the reference's loop is single-threaded (bvh-visualizer/main.cpp:60-78)"},
+            "primary_rays_only": {"value": cpu.primary_rays(2.0), "unit": UNIT, "cores": cpu.cores,
+                                  "sample": "bvh-visualizer pixel loop over the view's primary rays, tmax FLT_MAX (round 1's figure)"},
+            "full_path_port": {"value": port_value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": port_sample}}
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    import rayfinder_b200 as rf  # noqa: F401  (host-side .pt loader only)
-
-    pt, scene_name = load_scene()
-    cpu = CpuTraversal(pt, args.width, args.height)
+    cpu = CpuReference(args.width, args.height, args.bounces)
     # K timed steps + W warm-up steps must end within a few minutes: bound each step's sample
     budget = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
-    rows = cpu.calibrate(budget)
-    for k in range(args.warmup):
-        cpu.run_sample(rows, offset=k)
+    passes = cpu.calibrate(budget)
+    for _ in range(args.warmup):
+        cpu.trace(passes)
     rays = secs = 0.0
-    for k in range(args.steps):
-        r, s = cpu.run_sample(rows, offset=k)
+    for _ in range(args.steps):
+        r, s = cpu.trace(passes)
         rays += r
         secs += s
     value = rays / secs / 1e6
+    port_value, port_sample, frame_rays = cpu.full_path_port()  # (also the exact ray count of the frame, as the GPU arm reports it)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "Sponza.pt baked from the reference's assets/Sponza.glb",
-        "config": {"workload": workload_name(scene_name, args.width, args.height, args.bounces),
-                   "note": "reference CPU path = bvh-visualizer traversal of the primary rays (the reference has no CPU path tracer)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample_description(rows)},
+        "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE,
+        "config": base_config(args.width, args.height, args.bounces, frame_rays, args.width * args.height, "host caches, not flushed",
+                              f"reference CPU rayIntersectBvh over a bounded sample of the frame's rays per step, {cpu.cores} host threads",
+                              "host only (rank 0)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample_description(passes),
+                         "full_path_port": {"value": port_value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": port_sample}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -263,6 +290,78 @@ def run_reference(args, rank: int):
 
 
 # ---- this repo's CUDA path ----------------------------------------------------------------------------------
+def load_scene():
+    from rayfinder_b200 import assets as rfa
+
+    if rfa.scene_path("Sponza") is None:
+        raise SystemExit("bench.py: assets/Sponza.pt[.xz] is missing (bake it with __graft_entry__.build() where the reference is mounted)")
+    return rfa.load_scene("Sponza")
+
+
+def ncu_reference(world: int, w: int, h: int) -> dict | None:
+    """The committed ncu capture this line's roofline refers to: profiles/r02_roofline_ncu.json holds, per frame share
+    (key = pixels a GPU owns), the dominant kernel's per-launch DRAM/L2 traffic and its pipe utilisations."""
+    path = ROOT / "profiles" / "r02_roofline_ncu.json"
+    if not path.exists():
+        return None
+    table = json.loads(path.read_text())
+    return table.get("captures", {}).get(f"{w}x{h}/{world}")
+
+
+def build_roofline(args, world, stats, stage_stats, clocks, num_sms, w, h):
+    """roofline of the dominant kernel (k_trace, rank 0's launches).  Two denominators:
+    * the contract's: algorithmic bytes (48 B per node visited + 48 B per triangle tested, counted exactly by
+      the kernel) / launch time against the measured HBM copy bandwidth -> `hbm_algorithmic_frac`.  The 28.7 MB node +
+      triangle set is L1/L2-resident, so this exceeds 1: HBM is not what bounds the kernel (DRAM traffic per launch is ~1% of
+      the algorithmic bytes, `traffic`).
+    * the binding one: the SM's L1TEX stage accepts one wavefront (one 128-byte line of one request) per clock.  Every node
+      record a lane loads and each of the three 16-byte rows of a triangle is one wavefront (divergent lanes, distinct
+      lines), the kernel counts those loads exactly, so achieved = wavefronts / launch time and peak = SMs x SM clock
+      (the clock sampled under load)."""
+    peaks = {}
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peaks = json.loads(peaks_path.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bounces = args.bounces
+    nodes = stage_stats["closest_nodes_visited"] + stage_stats["shadow_nodes_visited"]
+    tris = stage_stats["closest_triangles_tested"] + stage_stats["shadow_triangles_tested"]
+    node_loads = stage_stats.get("node_records_loaded") or nodes
+    trace_ms = stage_stats["device_ms_trace"]
+    launches = args.steps * (bounces + 1)
+    if trace_ms <= 0:
+        return {"bound": "l1tex", "kernel": "k_trace", "achieved": None, "peak": None, "unit": "Gwavefronts/s", "frac": None, "traffic": None}
+    seconds = trace_ms * 1e-3
+    algorithmic = 48 * (nodes + tris)
+    hbm_achieved = algorithmic / seconds / 1e9
+    wavefronts = node_loads + 3 * tris
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    l1_peak = num_sms * sm_mhz * 1e6 / 1e9          # Gwavefronts/s
+    l1_achieved = wavefronts / seconds / 1e9
+    ncu = ncu_reference(world, w, h)
+    out = {
+        "bound": "l1tex", "kernel": "k_trace", "achieved": l1_achieved, "peak": l1_peak, "unit": "Gwavefronts/s", "frac": l1_achieved / l1_peak,
+        "traffic": ncu.get("dram_bytes_per_launch") if ncu else None,
+        "lts_bytes_per_launch": ncu.get("lts_bytes_per_launch") if ncu else None,
+        "ncu": ncu,
+        "hbm_algorithmic_frac": hbm_achieved / hbm_peak, "hbm_algorithmic_achieved_gbs": hbm_achieved, "hbm_peak_gbs": hbm_peak,
+        "hbm_peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
+        "note": ("bound = the L1TEX wavefront stage (1 wavefront / clk / SM): wavefronts = node records loaded + 3 x triangles tested, "
+                 "counted by the kernel; peak = SMs x SM clock under load.  hbm_algorithmic_* is the contract figure (48 B per node visit "
+                 "+ 48 B per triangle test over the measured HBM copy bandwidth): it exceeds 1 because the 28.7 MB working set is cache-"
+                 "resident — HBM does not bound this kernel (traffic = DRAM bytes per launch from the committed ncu capture)"),
+        "algorithmic_bytes_per_launch": algorithmic / launches, "wavefronts_per_launch": wavefronts / launches,
+        "avg_launch_ms": trace_ms / launches, "launches": launches,
+        "stage_ms_per_step": {k: stage_stats[f"device_ms_{k}"] / args.steps for k in ("trace", "shade", "other")},
+        "stage_loop_ms_per_step": stage_stats["device_ms_total"] / args.steps,
+        "stage_loop_schedule": "one tile set on one stream, one launch per stage (stage events need the stages back to back); "
+                               f"`value` is measured with the automatic schedule ({stats['sub_frames']} tile set(s))",
+        "mean_nodes_per_closest_ray": stats["closest_nodes_visited"] / max(1, stats["closest_rays"]),
+        "mean_nodes_per_shadow_ray": stats["shadow_nodes_visited"] / max(1, stats["shadow_rays"]),
+    }
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -278,16 +377,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    pt, scene_name = load_scene()
+    pt = load_scene()
     w, h, bounces = args.width, args.height, args.bounces
-    cam = rf.fly_camera(w, h) if scene_name.startswith("Sponza") else rf.bvh_visualizer_camera(pt.bvh_nodes, w, h)
+    cam = rf.fly_camera(w, h)
     params = rf.RenderParameters((w, h), cam, rf.SamplingParams(1, bounces), rf.Sky(), 0.25)
     ren = rf.ReferencePathTracer(params, (w, h), rf.SceneArrays.from_pt(pt), device=local_rank)
     ren.set_tile_partition(rank, world)
     stream = torch.cuda.current_stream(dev)
     ren.set_stream(stream.cuda_stream)
-    exchange = rfd.HdrExchange(ren, w, h, mode=os.environ.get("RF_EXCHANGE", "auto"))
-    hdr = exchange.hdr
+    exchange = rfd.HdrExchange(ren, w, h, mode=args.exchange)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_hdr = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
     host_np = host_hdr.numpy()
@@ -305,14 +403,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def step_device():
         new_frame()
         ren.render()
-        exchange()
+        return exchange()
 
     def step_e2e():
         new_frame()  # host -> device: the render parameters (uniform block) travel with the launch
         ren.render()
-        exchange()
+        full = exchange()
         if rank == 0:
-            ren.read_hdr(host_np)  # device -> host: the HDR image
+            # device -> host: the HDR image (the exchanged frame on the root of a multi-GPU run)
+            host_hdr.copy_(full, non_blocking=True)
+            stream.synchronize()
         else:
             ren.synchronize()
 
@@ -346,7 +446,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- per-kernel timing for the roofline: the same K steps with CUDA events between the stages.  Stage events
     #      need the stages back to back on one stream, so this loop runs the frame as one tile set (the default
-    #      overlaps two tile sets on two streams, which is what `value` measures). ----
+    #      may overlap two tile sets on two streams, which is what `value` measures). ----
     ren.set_pipeline(1)
     ren.set_stage_timing(True)
     step_device()
@@ -370,6 +470,28 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     e2e_seconds = time.perf_counter() - t0
 
+    # ---- parity of the multi-GPU frame: the exchanged image on rank 0 against one untimed single-GPU render of the
+    #      same frame on rank 0, bit for bit ----
+    parity = None
+    if world > 1:
+        exchanged = step_device()
+        barrier()
+        if rank == 0:
+            multi = exchanged.cpu().numpy().copy()
+        exchange_mode = exchange.mode
+        exchange.close()
+        if rank == 0:
+            ren.set_tile_partition(0, 1)
+            new_frame()
+            ren.render()
+            single, _ = ren.read_hdr()
+            parity = {"bit_identical_to_1gpu": bool(np.array_equal(multi.view(np.uint32), single.view(np.uint32))), "mode": exchange_mode,
+                      "pixels_compared": int(w * h), "max_abs_diff": float(np.max(np.abs(multi[..., :3] - single[..., :3])))}
+        barrier()
+    else:
+        exchange_mode = exchange.mode
+        exchange.close()
+
     rays_local = stats["closest_rays"] + stats["shadow_rays"]
     agg = torch.tensor([ms_total, e2e_seconds], dtype=torch.float64, device=dev)
     cnt = torch.tensor([rays_local, stats["paths"]], dtype=torch.int64, device=dev)
@@ -380,54 +502,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     rays_total, paths_total = int(cnt[0]), int(cnt[1])
 
     if rank == 0:
-        peaks = {}
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peaks = json.loads(peaks_path.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: k_trace (rank 0's launches): closest-hit + shadow rays share the traversal launches.
-        # Algorithmic bytes: 48 B per node visited + 48 B per triangle tested.
-        nodes = stage_stats["closest_nodes_visited"] + stage_stats["shadow_nodes_visited"]
-        tris = stage_stats["closest_triangles_tested"] + stage_stats["shadow_triangles_tested"]
-        trace_bytes = 48 * (nodes + tris)
-        trace_ms = stage_stats["device_ms_trace"]
-        launches = args.steps * (bounces + 1)
-        achieved = trace_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
-        traffic = None
-        traffic_files = sorted((ROOT / "profiles").glob("r*_k_trace_traffic.json"))
-        if traffic_files:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
-            traffic = json.loads(traffic_files[-1].read_text()).get("dram_bytes_per_launch_mean")
-        packed = 32 * nodes + 48 * tris
-        roofline = {
-            "bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-            "frac_packed_layout": (packed / (trace_ms * 1e-3) / 1e9 / peak) if achieved else None,
-            "note": ("algorithmic bytes = 48 B per node visit + 48 B per triangle test (SURVEY.md 8(d)); the 28.7 MB "
-                     "node+triangle set is L1/L2-resident, so DRAM traffic is ~1% of the algorithmic bytes and the binding "
-                     "resources are SM issue slots and the L1 tag stage (profiles/)"),
-            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
-            "algorithmic_bytes_per_launch": trace_bytes / launches, "avg_launch_ms": trace_ms / launches,
-            "launches": launches, "packed_bytes_per_launch": packed / launches,
-            "stage_ms_per_step": {k: stage_stats[f"device_ms_{k}"] / args.steps for k in ("trace", "shade", "other")},
-            "stage_loop_ms_per_step": stage_stats["device_ms_total"] / args.steps,
-            "mean_nodes_per_closest_ray": stats["closest_nodes_visited"] / max(1, stats["closest_rays"]),
-            "mean_nodes_per_shadow_ray": stats["shadow_nodes_visited"] / max(1, stats["shadow_rays"]),
-        }
+        num_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        roofline = build_roofline(args, world, stats, stage_stats, clocks, num_sms, w, h)
         value = rays_total / (ms_total * 1e-3) / 1e6
+        pipeline = (f"{stats['sub_frames']} tile set(s) on separate CUDA streams, one launch per stage (raygen, {bounces + 1} x trace, "
+                    f"{bounces} x shade, accumulate per set)"
+                    + (f"; each trace launch hands warps left with <= {stats['evict_max']} rays to a warp-per-ray tail launch"
+                       if stats["evict_max"] else ""))
+        partition = (f"32x32 tiles, (tx+ty) % {world}; exchange per step: "
+                     + ("owned pixels stored into rank 0's double-buffered exchange target over NVLink peer memory by the accumulation "
+                        "kernel + a 4-byte all-reduce as frame barrier" if exchange_mode == "p2p"
+                        else "one out-of-place NCCL sum-reduce of the HDR buffer")) if world > 1 else "single GPU"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "Sponza.pt baked from the reference's assets/Sponza.glb (deterministic asset, not synthetic)",
-            "config": {"workload": workload_name(scene_name, w, h, bounces), "rays_per_step": rays_total // args.steps,
-                       "paths_per_step": paths_total // args.steps, "l2": "flushed between timed iterations (256 MiB memset)",
-                       "pipeline": (f"{stats['sub_frames']} tile set(s) on separate CUDA streams, one launch per stage (raygen, {bounces + 1} x trace, "
-                                    f"{bounces} x shade, accumulate per set)"
-                                    + (f"; each trace launch hands warps left with <= {stats['evict_max']} rays to a warp-per-ray tail launch"
-                                       if stats["evict_max"] else "")),
-                       "partition": (f"32x32 tiles, (tx+ty) % {world}; exchange per step: "
-                                     + ("owned pixels stored into rank 0's HDR buffer over NVLink peer memory by the accumulation kernel + a 4-byte "
-                                        "all-reduce as frame barrier" if exchange.mode == "p2p" else "one NCCL sum-reduce of the HDR buffer"))
-                       if world > 1 else "single GPU"},
+            "dtype": "f32", "data": DATA_NOTE,
+            "config": base_config(w, h, bounces, rays_total // args.steps, paths_total // args.steps,
+                                  "flushed between timed iterations (256 MiB memset)", pipeline, partition),
             "clocks": clocks,
             "e2e": {"value": rays_total / e2e_seconds / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": w * h * 16, "ms_per_step": 1e3 * e2e_seconds / args.steps},
@@ -435,15 +526,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "roofline": roofline,
             "library": {"path": str(capi.LIB_PATH.relative_to(ROOT)), "build": capi.lib().rf_build_info().decode()},
         }
+        if parity is not None:
+            line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            cpu = CpuTraversal(pt, w, h)
-            rows = cpu.calibrate(args.cpu_seconds)
-            r, s = cpu.run_sample(rows)
-            line["cpu_baseline"] = {"value": r / s / 1e6, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
-                                    "sample": cpu.sample_description(rows)}
+            line["cpu_baseline"] = cpu_baseline_block(CpuReference(w, h, bounces), args.cpu_seconds)
         print(json.dumps(line), flush=True)
 
-    exchange.close()
     ren.close()
     if world > 1:
         dist.destroy_process_group()

@@ -176,6 +176,9 @@ struct Counters
 {
     std::uint64_t closestRays = 0, shadowRays = 0, closestNodes = 0, closestTris = 0, shadowNodes = 0, shadowTris = 0;
     std::uint64_t paths = 0;
+    // optional log of every ray rayColor traces: (origin, direction) + kind (0 closest-hit, 1 shadow); see oracle_frame_rays
+    std::vector<float>*        rayLog = nullptr;
+    std::vector<std::uint8_t>* rayKind = nullptr;
 };
 
 // Scene view used by both oracles.  `triStride` = floats per vertex (3: nlrs::Positions, 4:
@@ -434,6 +437,13 @@ vec3 rayColor(
     {
         Intersection hit;
         ++ctr.closestRays;
+        const auto logRay = [&ctr](const Ray& r, std::uint8_t kind) {
+            if (!ctr.rayLog) return;
+            const float six[6] = {r.origin.x, r.origin.y, r.origin.z, r.direction.x, r.direction.y, r.direction.z};
+            ctr.rayLog->insert(ctr.rayLog->end(), six, six + 6);
+            if (ctr.rayKind) ctr.rayKind->push_back(kind);
+        };
+        logRay(ray, 0);
         if (rayIntersectBvh(scene, ray, T_MAX, &hit, nullptr, nullptr, ctr.closestNodes, ctr.closestTris))
         {
             const vec3 albedo = textureLookup(scene, hit.textureDescriptorIdx, hit.uv);
@@ -444,6 +454,7 @@ vec3 rayColor(
             const vec3  brdf = albedo * FRAC_1_PI;
             const vec3  reflectance = brdf * dot(hit.n, lightDirection);
             ++ctr.shadowRays;
+            logRay(Ray{p, lightDirection}, 1);
             const float lightVisibility = shadowRay(scene, Ray{p, lightDirection}, T_MAX, ctr.shadowNodes, ctr.shadowTris);
             radiance = radiance + throughput * lightIntensity * reflectance * lightVisibility * k.solarInvPdf;
 
@@ -718,6 +729,67 @@ double oracle_render_frame(const OracleScene* sc, const OracleFrame* fr, float* 
         }
     }
     return seconds;
+}
+
+// The rays of one frame: runs fsMain/rayColor (as oracle_render_frame does) for the pixels of every `tileStride`-th 32x32
+// tile and logs every ray the path tracer traces for them — the closest-hit ray of each bounce and the shadow ray of each
+// hit — as 6 floats (origin, direction) in `outRays` and its kind (0 closest-hit, 1 shadow) in `outKind`, in path order per
+// pixel.  Returns the number of rays (at most `capacity` are written).  This is the ray set bench.py hands to the
+// reference's own CPU rayIntersectBvh, so that the CPU arm traces the same workload as the GPU arm.
+std::uint64_t oracle_frame_rays(
+    const OracleScene* sc, const OracleFrame* fr, std::uint32_t tileStride, float* outRays, std::uint8_t* outKind, std::uint64_t capacity, int numThreads)
+{
+    std::vector<float> bn(128 * 128 * 2);
+    for (std::size_t i = 0; i < bn.size(); ++i) bn[i] = static_cast<float>(sc->blueNoiseRg8[i]) / 255.0f;
+    SceneView scene{};
+    scene.nodes = static_cast<const BvhNode*>(sc->nodes);
+    scene.tris = sc->positionAttributes;
+    scene.triStride = 4;
+    scene.vattr = static_cast<const VertexAttributes*>(sc->vertexAttributes);
+    scene.texDesc = sc->texDesc;
+    scene.numTextures = sc->numTextures;
+    scene.texels = sc->texels;
+    scene.numTexels = sc->numTexels;
+    scene.blueNoise = bn.data();
+    scene.bnWidth = 128, scene.bnHeight = 128;
+    Camera camera;
+    std::memcpy(&camera, fr->camera, sizeof(Camera));
+    SkyState sky;
+    std::memcpy(&sky, fr->skyState, sizeof(SkyState));
+    const std::uint32_t W = fr->width, H = fr->height, tilesX = (W + 31u) / 32u;
+    if (numThreads < 1) numThreads = 1;
+    if (tileStride < 1) tileStride = 1;
+    // one log per image row, concatenated in row order afterwards: the result does not depend on the thread count
+    std::vector<std::vector<float>>        rowRays(H);
+    std::vector<std::vector<std::uint8_t>> rowKind(H);
+    parallelRows(0, static_cast<int>(H), numThreads, [&](int py, int) {
+        Counters ctr;
+        ctr.rayLog = &rowRays[py];
+        ctr.rayKind = &rowKind[py];
+        for (std::uint32_t px = 0; px < W; ++px)
+        {
+            const float         u = (static_cast<float>(px) + 0.5f) / static_cast<float>(W);
+            const float         v = (static_cast<float>(py) + 0.5f) / static_cast<float>(H);
+            const std::uint32_t cx = static_cast<std::uint32_t>(u * static_cast<float>(W));
+            const std::uint32_t cy = static_cast<std::uint32_t>(v * static_cast<float>(H));
+            if (((cy / 32u) * tilesX + (cx / 32u)) % tileStride != 0u) continue;
+            float blueNoise[2];
+            animatedBlueNoise(scene, cx, cy, fr->frameCount, fr->numSamplesPerPixel, blueNoise);
+            const float jx = blueNoise[0] / static_cast<float>(W), jy = blueNoise[1] / static_cast<float>(H);
+            const Ray   primaryRay = generateCameraRayWgsl(blueNoise, camera, u + jx, (1.0f - v) + jy);
+            rayColor(scene, sky, blueNoise, primaryRay, fr->numBounces, ctr);
+        }
+    });
+    std::uint64_t n = 0;
+    for (std::uint32_t y = 0; y < H; ++y)
+    {
+        const std::uint64_t rays = rowKind[y].size();
+        const std::uint64_t take = n + rays <= capacity ? rays : (capacity > n ? capacity - n : 0u);
+        if (take && outRays) std::memcpy(outRays + 6 * n, rowRays[y].data(), take * 6 * sizeof(float));
+        if (take && outKind) std::memcpy(outKind + n, rowKind[y].data(), take);
+        n += rays;
+    }
+    return n;
 }
 
 // ---- the deferred renderer's lighting pass: pt/deferred_renderer_lighting_pass.wgsl ------------------------------

@@ -66,6 +66,8 @@ def oracle() -> C.CDLL:
     lib.oracle_solar_constants.argtypes = [_P]
     lib.oracle_render_frame.restype = C.c_double
     lib.oracle_render_frame.argtypes = [C.POINTER(OracleScene), C.POINTER(OracleFrame), _P, _P, _P, C.c_int]
+    lib.oracle_frame_rays.restype = C.c_uint64
+    lib.oracle_frame_rays.argtypes = [C.POINTER(OracleScene), C.POINTER(OracleFrame), C.c_uint32, _P, _P, C.c_uint64, C.c_int]
     lib.oracle_display.argtypes = [_P, C.c_uint64, C.c_float, C.c_float, _P]
     lib.oracle_deferred_lighting.restype = C.c_double
     lib.oracle_deferred_lighting.argtypes = [C.POINTER(OracleScene), C.POINTER(OracleDeferred), _P, _P, _P, _P, _P, C.c_int]
@@ -128,6 +130,110 @@ def tex_desc(textures) -> tuple[np.ndarray, np.ndarray]:
         desc.append((t.shape[1], t.shape[0], off))
         off += t.size
     return np.array(desc, dtype=np.uint32), np.concatenate([np.ascontiguousarray(t).reshape(-1) for t in textures]).astype("<u4")
+
+
+# ---- the reference arm's own scene loading and camera (no product code involved) ----------------------
+BVH_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("pad0", "<f4"), ("aabb_max", "<f4", 3), ("pad1", "<f4"),
+                           ("triangles_offset", "<u4"), ("second_child_offset", "<u4"), ("triangle_count", "<u4"),
+                           ("split_axis", "<u4")])  # common/bvh.hpp:13-21
+
+
+class NumpyPt:
+    """A .pt file read with numpy alone, following the layout of pt-format/pt_format.cpp:240-269 — the loader of
+    bench.py's reference arm, which must not map the product library."""
+
+    ELEM_SIZE = (48, 36, 48, 80, 16, 16, 8, 4, 16, 16, 16, 16, 4)
+
+    def __init__(self, raw: bytes):
+        if raw[:9] != b"PTFORMAT3":
+            raise ValueError("Invalid file format: expected PtFormat file.")
+        pos, arrays = 9, []
+        for size in self.ELEM_SIZE:
+            n = int(np.frombuffer(raw, "<u8", 1, pos)[0])
+            arrays.append(np.frombuffer(raw, np.uint8, n * size, pos + 8))
+            pos += 8 + n * size
+        self.bvh_nodes = arrays[0].view(BVH_NODE_DTYPE).copy()
+        self.bvh_position_attributes = arrays[1].view("<f4").reshape(-1, 9).copy()
+        self.triangle_position_attributes = arrays[2].view("<f4").reshape(-1, 12).copy()
+        self.triangle_vertex_attributes = arrays[3].view("<f4").reshape(-1, 20).copy()
+        self.base_color_textures = []
+        num_textures = int(np.frombuffer(raw, "<u8", 1, pos)[0])
+        pos += 8
+        for _ in range(num_textures):
+            w, h = (int(x) for x in np.frombuffer(raw, "<u4", 2, pos))
+            n = int(np.frombuffer(raw, "<u8", 1, pos + 8)[0])
+            self.base_color_textures.append(np.frombuffer(raw, "<u4", n, pos + 16).reshape(h, w).copy())
+            pos += 16 + 4 * n
+
+    @classmethod
+    def load_scene(cls, name: str) -> "NumpyPt | None":
+        for path in (ASSETS / f"{name}.pt", ASSETS / f"{name}.pt.xz"):
+            if path.exists():
+                raw = path.read_bytes()
+                return cls(lzma.decompress(raw) if path.suffix == ".xz" else raw)
+        return None
+
+
+def _degrees_to_radians(deg: float) -> np.float32:
+    return np.float32(np.float32(np.float32(deg) * np.float32(np.pi)) / np.float32(180.0))  # Angle::degrees, units/angle.hpp:12-15
+
+
+def fly_camera_array(width: int, height: int, position=(1.22, 1.25, -1.25), yaw_degrees=129.64, pitch_degrees=-13.73,
+                     vfov_degrees=70.0, aperture=0.0, focus_distance=10.0) -> np.ndarray:
+    """The benchmark view (fly_camera_controller.hpp:47-52, cameraOrientation :138-148, vfov 70 deg pt/main.cpp:49,314) as
+    the 19 floats of nlrs::Camera, built by the reference's own createCamera (oracle/_ref) or, without it, the port."""
+    import math
+
+    f32 = np.float32
+    yaw, pitch = _degrees_to_radians(yaw_degrees), _degrees_to_radians(pitch_degrees)
+    cy, sy, cp, sp = (f32(fn(float(a))) for fn, a in ((math.cos, yaw), (math.sin, yaw), (math.cos, pitch), (math.sin, pitch)))
+    fwd = np.array([cy * cp, sp, sy * cp], dtype=f32)
+    d = f32(f32(fwd[0] * fwd[0] + fwd[1] * fwd[1]) + fwd[2] * fwd[2])
+    fwd = fwd * f32(f32(1.0) / np.sqrt(d))
+    pos = np.array(position, dtype=f32)
+    look_at = (pos + f32(focus_distance) * fwd).astype(f32)
+    out = np.zeros(19, dtype=f32)
+    aspect = float(f32(width) / f32(height))
+    if have_ref():  # takes degrees: it calls Angle::degrees itself
+        ref().ref_create_camera(_ptr(pos), _ptr(look_at), float(aperture), float(focus_distance), float(vfov_degrees), aspect, _ptr(out))
+    else:
+        oracle().oracle_create_camera(_ptr(pos), _ptr(look_at), float(aperture), float(focus_distance),
+                                      float(_degrees_to_radians(vfov_degrees)), aspect, _ptr(out))
+    return out
+
+
+def default_sky_state() -> np.ndarray:
+    """AlignedSkyState(Sky{}) (aligned_sky_state.hpp:17-20, 43-70) as 40 floats, from the reference's sky_state_new when
+    oracle/_ref is built."""
+    import math
+
+    f32 = np.float32
+    zenith, azimuth = _degrees_to_radians(30.0), _degrees_to_radians(0.0)
+    out = np.zeros(40, dtype=f32)
+    if have_ref():
+        state = np.zeros(33, dtype=f32)  # params[27], sky_radiances[3], solar_radiances[3]
+        albedo = np.ones(3, dtype=f32)
+        ref().ref_sky_state_new(float(f32(0.5) * f32(np.pi) - zenith), 1.0, _ptr(albedo), _ptr(state))
+        out[:33] = state
+    else:
+        raise RuntimeError("default_sky_state needs oracle/_ref")
+    sin_z, cos_z = f32(math.sin(float(zenith))), f32(math.cos(float(zenith)))
+    d = np.array([sin_z * f32(math.cos(float(azimuth))), cos_z, -sin_z * f32(math.sin(float(azimuth)))], dtype=f32)
+    n = f32(f32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+    out[36:39] = d * f32(f32(1.0) / np.sqrt(n))
+    return out
+
+
+def frame_rays(pt, width, height, cam19, sky40, spp, bounces, tile_stride=1, frame_count=0, threads=None):
+    """(rays (n, 6) f32, kind (n,) u8: 0 closest-hit / 1 shadow) — every ray the path tracer traces for the pixels of every
+    ``tile_stride``-th 32x32 tile of the frame (oracle_frame_rays)."""
+    o = OracleRenderer(pt, width, height, cam19, sky40, spp, bounces, threads=threads)
+    fr = OracleFrame(width, height, frame_count, spp, bounces, 0, 0, 1, (C.c_float * 19)(*o.cam19), (C.c_float * 40)(*o.sky40))
+    n = oracle().oracle_frame_rays(C.byref(o.scene), C.byref(fr), tile_stride, None, None, 0, o.threads)
+    rays = np.zeros((n, 6), dtype=np.float32)
+    kind = np.zeros(n, dtype=np.uint8)
+    oracle().oracle_frame_rays(C.byref(o.scene), C.byref(fr), tile_stride, _ptr(rays), _ptr(kind), n, o.threads)
+    return rays, kind
 
 
 # ---- oracle wrappers ---------------------------------------------------------------------------------

@@ -1,15 +1,13 @@
 #!/usr/bin/env python3
 """Per-launch spans of one staged frame (one tile set, one stream) at a few frame sizes (GPU box).
 
-    RF_DEBUG_STAGES=1 python tools/stage_times.py [WxH ...]
+    python tools/stage_times.py [WxH ...]
 """
-import os
 import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-os.environ.setdefault("RF_DEBUG_STAGES", "1")
 
 import rayfinder_b200 as rf  # noqa: E402
 from rayfinder_b200 import assets as rfa  # noqa: E402
@@ -22,6 +20,7 @@ for size in (sys.argv[1:] or ["1920x1080", "672x384"]):
     ren = rf.ReferencePathTracer(params, (w, h), scene)
     ren.set_pipeline(1, 0, 3, 256)
     ren.set_stage_timing(True)
+    ren.set_option("stage_debug", 1)
     print(f"== {w}x{h}", file=sys.stderr, flush=True)
     for k in range(4):
         params.exposure = 0.25 + 0.01 * k
