@@ -187,6 +187,11 @@ typedef struct rf_frame_stats
     uint64_t kernel_launches;      /* kernels launched by rf_renderer_render since the last reset */
     uint32_t sub_frames;           /* schedule in effect: tile sets per frame, */
     uint32_t evict_max;            /* tail hand-over threshold (rf_renderer_set_pipeline / _set_tail_policy) */
+    uint64_t node_records_loaded;  /* BVH records the traversal kernels loaded: one 64-byte child-pair record per interior
+                                    * node a ray entered (csrc/traversal_pairs.cuh), or one 32-byte node per visit with the
+                                    * per-node kernel — the memory work behind the visits above */
+    uint32_t trace_kernel;         /* traversal kernel in effect: 2 = child-pair records, 1 = one node per visit */
+    uint32_t reserved;
 } rf_frame_stats;
 
 /* ---- the renderer: nlrs::ReferencePathTracer (pt/reference_path_tracer.hpp:59-102) ------------- */

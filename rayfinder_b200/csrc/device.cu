@@ -217,6 +217,18 @@ void launchTrace(int variant, int block, std::uint32_t stackEntries, Args&&... a
 }
 
 template<typename... Args>
+void launchTracePairs(int variant, int grid, cudaStream_t s, Args&&... args)
+{
+    switch (variant & 7)
+    {
+    case 1: k_trace_pairs<1, 256><<<grid, 256, 0, s>>>(args...); break;
+    case 5: k_trace_pairs<5, 256><<<grid, 256, 0, s>>>(args...); break;
+    case 7: k_trace_pairs<7, 256><<<grid, 256, 0, s>>>(args...); break;
+    default: k_trace_pairs<3, 256><<<grid, 256, 0, s>>>(args...); break;
+    }
+}
+
+template<typename... Args>
 void launchMega(int variant, int block, int grid, cudaStream_t s, Args&&... args)
 {
     if (block == 64)
@@ -243,6 +255,11 @@ struct rf_renderer
     DeviceBuffer<float4>        tris, vattr;
     bool                        ordered = true;
     TraceTuning                 tuning = defaultTuning();
+    DeviceBuffer<PairRecord>    pairRecords;  // child-pair records (pair_records.h); empty when the scene's leaves do not fit a link
+    PairSceneDevice             pairsDev{};
+    int                         traceKernel = 0;  // 0: automatic (pairs when the scene has them), 1: one node per visit, 2: pairs
+    int                         pairVariant = PAIR_DEFAULT_VARIANT;
+    bool                        usePairs() const { return pairsDev.records != nullptr && traceKernel != 1; }
     DeviceBuffer<uint4>         texDesc;
     DeviceBuffer<std::uint32_t> texels;
     DeviceBuffer<uchar2>        blueNoise;
@@ -500,7 +517,12 @@ struct rf_renderer
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
     std::uint32_t stragglerCapacity() const { return static_cast<std::uint32_t>(numSms) * 64u * 8u; }
-    std::uint32_t effectiveEvictMax() const { return evictMax >= 0 ? static_cast<std::uint32_t>(evictMax) : (smallFrame() ? 8u : 0u); }
+    // (the tail hand-over belongs to the per-node kernel; the pair kernel ends every ray on its lane)
+    std::uint32_t effectiveEvictMax() const
+    {
+        if (usePairs() && !megakernel) return 0u;
+        return evictMax >= 0 ? static_cast<std::uint32_t>(evictMax) : (smallFrame() ? 8u : 0u);
+    }
 };
 
 extern "C" rf_status rf_renderer_create(
@@ -566,6 +588,18 @@ extern "C" rf_status rf_renderer_create(
         k_pack_triangles<<<r->numSms * 4, 256>>>(rawTris.ptr, 4, numTris, r->tris.ptr);
         RF_CUDA(cudaGetLastError());
         RF_CUDA(cudaDeviceSynchronize());
+    }
+    {
+        const PairScene ps = buildPairRecords(scene->bvh_nodes, numNodes);
+        if (ps.usable)
+        {
+            RF_CUDA(r->pairRecords.allocate(ps.records.size() + 1)); // (+1: a single-leaf tree has no record)
+            if (!ps.records.empty())
+                RF_CUDA(cudaMemcpy(r->pairRecords.ptr, ps.records.data(), ps.records.size() * sizeof(PairRecord), cudaMemcpyHostToDevice));
+            r->pairsDev.records = r->pairRecords.ptr;
+            std::memcpy(r->pairsDev.rootBox, ps.rootBox, sizeof(ps.rootBox));
+            r->pairsDev.rootLink = ps.rootLink;
+        }
     }
     RF_CUDA(r->vattr.allocate(5 * numTris));
     RF_CUDA(cudaMemcpy(r->vattr.ptr, scene->vertex_attributes, numTris * sizeof(rf_vertex_attributes), cudaMemcpyHostToDevice));
@@ -662,7 +696,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     fp.solarInvPdf = sc.invPdf;
 
     SceneDevice scene{r->nodes.ptr, r->tris.ptr, r->vattr.ptr, r->texDesc.ptr, r->texels.ptr, r->blueNoise.ptr, r->lut.ptr, r->srgbLut.ptr,
-                      r->ordered, r->tuning};
+                      r->ordered, r->tuning, r->pairsDev};
 
     rf_renderer::Timed t{};
     if (!r->eventPool.empty())
@@ -705,7 +739,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     RF_CUDA(cudaEventRecord(r->forkEvent, s));
 
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
+    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->traceBlocksPerSm) : r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
     RF_CUDA(stageMark());
     for (int i = 0; i < r->numSubFrames; ++i)
     {
@@ -762,8 +796,12 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         k_raygen<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
         RF_CUDA(stageMark());
         // closest-hit rays of bounce 1
-        launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0],
-                    stragglersOf(0), r->stats.ptr);
+        const bool pairsKernel = r->usePairs();
+        if (pairsKernel)
+            launchTracePairs(r->pairVariant, gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0], r->stats.ptr);
+        else
+            launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, ss, sfp, scene, sf.queues[0], &ctr[0], sf.hits.ptr, sf.queues[0], nullptr, r->radiance.ptr, &cursors[0],
+                        stragglersOf(0), r->stats.ptr);
         finishStragglers(0, sf.queues[0], sf.queues[0]);
         for (std::uint32_t bounce = 1; bounce <= fp.numBounces; ++bounce)
         {
@@ -773,8 +811,12 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             RF_CUDA(stageMark());
             // shadow rays of this bounce + closest-hit rays of the next one (none after the last bounce)
             const bool last = bounce == fp.numBounces;
-            launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
-                        r->radiance.ptr, &cursors[bounce], stragglersOf(bounce), r->stats.ptr);
+            if (pairsKernel)
+                launchTracePairs(r->pairVariant, gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
+                                 r->radiance.ptr, &cursors[bounce], r->stats.ptr);
+            else
+                launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, ss, sfp, scene, sf.queues[outQ], last ? nullptr : &ctr[bounce], sf.hits.ptr, sf.queues[outQ], &ctr[bounce],
+                            r->radiance.ptr, &cursors[bounce], stragglersOf(bounce), r->stats.ptr);
             finishStragglers(bounce, sf.queues[outQ], sf.queues[outQ]);
         }
         RF_CUDA(stageMark());
@@ -864,7 +906,7 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     fp.solarInvPdf = sc.invPdf;
     fp.deferred = 1u;
     SceneDevice scene{r->nodes.ptr, r->tris.ptr, r->vattr.ptr, r->texDesc.ptr, r->texels.ptr, r->blueNoise.ptr, d.lutRow.ptr, r->srgbLut.ptr,
-                      r->ordered, r->tuning};
+                      r->ordered, r->tuning, r->pairsDev};
     DeferredUniforms un{};
     std::memcpy(un.inverseViewReverseZProjection, p->inverse_view_reverse_z_projection, sizeof(un.inverseViewReverseZProjection));
     std::memcpy(un.cameraEye, p->camera_eye, sizeof(un.cameraEye));
@@ -891,14 +933,20 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     std::uint32_t* const cursors = ctr + 2;
     const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u, 0u};
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
+    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->traceBlocksPerSm) : r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
     RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(1) * sizeof(std::uint32_t), s));
     k_deferred_primary<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, un, d.albedo.ptr, d.normal.ptr, d.depth.ptr, queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
     // shadow rays of the G-buffer surfaces + the bounce rays
-    launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, s, fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[0], &ctr[0], r->radiance.ptr, &cursors[0], noHandOver, r->stats.ptr);
+    if (r->usePairs())
+        launchTracePairs(r->pairVariant, gridTrace, s, fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[0], &ctr[0], r->radiance.ptr, &cursors[0], r->stats.ptr);
+    else
+        launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, s, fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[0], &ctr[0], r->radiance.ptr, &cursors[0], noHandOver, r->stats.ptr);
     k_shade<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, queues[0], &ctr[0], d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr);
     // shadow rays of the bounce hits
-    launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], noHandOver, r->stats.ptr);
+    if (r->usePairs())
+        launchTracePairs(r->pairVariant, gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], r->stats.ptr);
+    else
+        launchTrace(r->variant, r->traceBlock, r->traceStackEntries(), gridTrace, s, fp, scene, queues[1], nullptr, d.hits.ptr, queues[1], &ctr[1], r->radiance.ptr, &cursors[1], noHandOver, r->stats.ptr);
     k_deferred_resolve<<<gridLight, BLOCK_THREADS, 0, s>>>(static_cast<std::uint32_t>(numPixels), p->frame_count, r->radiance.ptr, d.accumulation.ptr);
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventRecord(t.end, s));
@@ -1033,6 +1081,8 @@ extern "C" rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out)
     out->kernel_launches = r->kernelLaunches;
     out->sub_frames = static_cast<std::uint32_t>(r->numSubFrames);
     out->evict_max = r->megakernel ? 0u : r->effectiveEvictMax();
+    out->node_records_loaded = s[STAT_RECORDS];
+    out->trace_kernel = r->usePairs() && !r->megakernel ? 2u : 1u;
     return RF_OK;
 }
 
@@ -1161,6 +1211,8 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
     if (key == "shade_wait") r->tuning.shadeWait = static_cast<std::uint32_t>(value);
     else if (key == "evict_delay") r->evictDelay = static_cast<std::uint32_t>(value);
     else if (key == "trace_stack") r->forcedStackEntries = static_cast<std::uint32_t>(std::min<std::int64_t>(value, RF_STACK_SIZE));
+    else if (key == "trace_kernel" && value <= 2) r->traceKernel = static_cast<int>(value);
+    else if (key == "pair_variant" && value <= 7) r->pairVariant = static_cast<int>(value);
     else if (key == "stage_debug") r->stageDebug = value != 0;
     else if (key == "mega_debug") r->megaDebug = value != 0;
     else return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: unknown option '%s'", name);
@@ -1190,6 +1242,8 @@ struct rf_traversal_scene
     bool                        ordered = true;
     TraceTuning                 tuning = defaultTuning();
     std::uint64_t               numNodes = 0, numTris = 0;
+    DeviceBuffer<PairRecord>    pairRecords; // child-pair records (pair_records.h) when the scene's leaves fit a link
+    PairSceneDevice             pairsDev{};
 };
 
 extern "C" rf_status rf_traversal_scene_create(
@@ -1222,6 +1276,16 @@ extern "C" rf_status rf_traversal_scene_create(
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaDeviceSynchronize());
     s->numNodes = numNodes, s->numTris = numTriangles;
+    const PairScene ps = buildPairRecords(nodes, numNodes);
+    if (ps.usable)
+    {
+        RF_CUDA(s->pairRecords.allocate(ps.records.size() + 1));
+        if (!ps.records.empty())
+            RF_CUDA(cudaMemcpy(s->pairRecords.ptr, ps.records.data(), ps.records.size() * sizeof(PairRecord), cudaMemcpyHostToDevice));
+        s->pairsDev.records = s->pairRecords.ptr;
+        std::memcpy(s->pairsDev.rootBox, ps.rootBox, sizeof(ps.rootBox));
+        s->pairsDev.rootLink = ps.rootLink;
+    }
     *out = s.release();
     return RF_OK;
 }
@@ -1257,9 +1321,14 @@ extern "C" rf_status rf_ray_intersect_bvh(
     const std::uint64_t blocksNeeded = (numRays + TRACE_BLOCK_THREADS - 1) / TRACE_BLOCK_THREADS;
     const int           grid = static_cast<int>(std::min<std::uint64_t>(blocksNeeded, static_cast<std::uint64_t>(s->numSms) * 4));
     RF_CUDA(cudaMemset(s->cursor.ptr, 0, sizeof(std::uint32_t)));
-    k_intersect_batch<<<grid, TRACE_BLOCK_THREADS>>>(
-        s->nodes.ptr, s->tris.ptr, s->ordered, s->tuning, dRays.ptr, static_cast<std::uint32_t>(numRays), rayTMax, s->cursor.ptr,
-        dHit.ptr, dPT.ptr, dNodes.ptr);
+    if (s->pairsDev.records)
+        k_intersect_batch_pairs<<<grid, TRACE_BLOCK_THREADS>>>(
+            s->pairsDev, s->tris.ptr, s->ordered, s->tuning, dRays.ptr, static_cast<std::uint32_t>(numRays), rayTMax, s->cursor.ptr, dHit.ptr, dPT.ptr,
+            dNodes.ptr);
+    else
+        k_intersect_batch<<<grid, TRACE_BLOCK_THREADS>>>(
+            s->nodes.ptr, s->tris.ptr, s->ordered, s->tuning, dRays.ptr, static_cast<std::uint32_t>(numRays), rayTMax, s->cursor.ptr,
+            dHit.ptr, dPT.ptr, dNodes.ptr);
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaDeviceSynchronize());
     if (outHit) RF_CUDA(cudaMemcpy(outHit, dHit.ptr, numRays, cudaMemcpyDeviceToHost));
@@ -1319,8 +1388,12 @@ extern "C" rf_status rf_bvh_visualizer_node_counts(
     RF_CUDA(cudaEventCreate(&e1));
     RF_CUDA(cudaMemset(s->cursor.ptr, 0, sizeof(std::uint32_t)));
     RF_CUDA(cudaEventRecord(e0));
-    k_visualizer<<<s->numSms * 4, TRACE_BLOCK_THREADS>>>(
-        s->nodes.ptr, s->tris.ptr, s->ordered, s->tuning, *camera, width, height, rayTMax, s->cursor.ptr, dNodes.ptr);
+    if (s->pairsDev.records)
+        k_visualizer_pairs<<<s->numSms * 4, TRACE_BLOCK_THREADS>>>(
+            s->pairsDev, s->tris.ptr, s->ordered, s->tuning, *camera, width, height, rayTMax, s->cursor.ptr, dNodes.ptr);
+    else
+        k_visualizer<<<s->numSms * 4, TRACE_BLOCK_THREADS>>>(
+            s->nodes.ptr, s->tris.ptr, s->ordered, s->tuning, *camera, width, height, rayTMax, s->cursor.ptr, dNodes.ptr);
     RF_CUDA(cudaEventRecord(e1));
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaDeviceSynchronize());

@@ -14,6 +14,7 @@
 #include "rf_internal.h"
 #include "straggler.cuh"
 #include "traversal.cuh"
+#include "traversal_pairs.cuh"
 
 namespace rfb200
 {
@@ -61,6 +62,7 @@ struct SceneDevice
     const float*         srgbLut;    // 256
     bool                 ordered;    // every node box finite with min <= max (enables the NaN-free slab test)
     TraceTuning          tuning;
+    PairSceneDevice      pairs;      // child-pair records (records == nullptr: the scene has none, see pair_records.h)
 };
 
 // Device counters (u32 array, zeroed once at the start of every frame):
@@ -80,6 +82,7 @@ enum StatSlot
     STAT_CLOSEST_TRIS,
     STAT_SHADOW_NODES,
     STAT_SHADOW_TRIS,
+    STAT_RECORDS, // BVH records loaded by the traversal kernels (pair records, or nodes with the per-node kernel)
     STAT_COUNT
 };
 
@@ -471,6 +474,40 @@ __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_tr
     {
         const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};
         atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(blockStats[threadIdx.x]));
+        if (threadIdx.x == 1 || threadIdx.x == 4) atomicAdd(&stats[STAT_RECORDS], static_cast<unsigned long long>(blockStats[threadIdx.x])); // one node per visit
+    }
+}
+
+// The traversal launch over child-pair records (traversal_pairs.cuh): same work items, same IO, same results.
+template<int VARIANT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_trace_pairs(
+    const __grid_constant__ FrameParams fp,
+    const __grid_constant__ SceneDevice scene,
+    const PathQueue      closestQueue,
+    const std::uint32_t* __restrict__ closestCount, // nullptr: no closest-hit rays in this launch
+    HitRecord*           hits,
+    const PathQueue      shadowQueue,
+    const std::uint32_t* __restrict__ shadowCount,  // nullptr: no shadow rays in this launch
+    float4*              radiance,
+    std::uint32_t*       fetchCursor,
+    unsigned long long*  stats)
+{
+    __shared__ std::uint32_t blockStats[7];
+    if (threadIdx.x < 7) blockStats[threadIdx.x] = 0u;
+    __syncthreads();
+    const std::uint32_t numClosest = closestCount ? *closestCount : 0u;
+    const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
+    TraceIO io{{fetchCursor, numClosest + numShadow}, StragglerBuffer{nullptr, nullptr, 0u, 0u, 0u}, fp, scene, closestQueue, numClosest, hits, shadowQueue,
+                  radiance, v3(fp.sky.sun_direction), blockStats};
+    std::uint32_t records = 0;
+    traceRaysPairs<2, VARIANT, BLOCK>(scene.pairs, scene.tris, scene.ordered, scene.tuning, io, records);
+    records = __reduce_add_sync(0xFFFFFFFFu, records);
+    if (laneId() == 0u) atomicAdd(&blockStats[6], records);
+    __syncthreads();
+    if (threadIdx.x < 7 && blockStats[threadIdx.x] != 0u)
+    {
+        const int slot[7] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS, STAT_RECORDS};
+        atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(blockStats[threadIdx.x]));
     }
 }
 
@@ -523,6 +560,7 @@ __global__ void __launch_bounds__(STRAGGLER_BLOCK_THREADS) k_trace_stragglers(
     {
         const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};
         atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(blockStats[threadIdx.x]));
+        if (threadIdx.x == 1 || threadIdx.x == 4) atomicAdd(&stats[STAT_RECORDS], static_cast<unsigned long long>(blockStats[threadIdx.x]));
     }
 }
 
@@ -670,6 +708,24 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer(
     traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, tuning, io);
 }
 
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_visualizer_pairs(
+    const __grid_constant__ PairSceneDevice pairs,
+    const float4* __restrict__ tris,
+    const bool          ordered,
+    const TraceTuning   tuning,
+    const rf_camera     camera,
+    const std::uint32_t width,
+    const std::uint32_t height,
+    const float         rayTMax,
+    std::uint32_t*      cursor,
+    std::uint32_t*      outNodes)
+{
+    const std::uint32_t blocksX = (width + 7u) / 8u, blocksY = (height + 3u) / 4u;
+    VisualizerIO        io{{cursor, blocksX * blocksY * 32u}, camera, width, height, blocksX, rayTMax, outNodes};
+    std::uint32_t       records = 0;
+    traceRaysPairs<0, PAIR_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(pairs, tris, ordered, tuning, io, records);
+}
+
 struct BatchIO : CursorSource
 {
     const float*   rays;
@@ -718,5 +774,23 @@ __global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch(
 {
     BatchIO io{{cursor, numRays}, rays, tris, rayTMax, outHit, outPT, outNodes};
     traceRays<0, TRACE_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(nodes, tris, ordered, tuning, io);
+}
+
+__global__ void __launch_bounds__(TRACE_BLOCK_THREADS) k_intersect_batch_pairs(
+    const __grid_constant__ PairSceneDevice pairs,
+    const float4* __restrict__ tris,
+    const bool          ordered,
+    const TraceTuning   tuning,
+    const float* __restrict__ rays,
+    const std::uint32_t numRays,
+    const float         rayTMax,
+    std::uint32_t*      cursor,
+    std::uint8_t*       outHit,
+    float4*             outPT,
+    std::uint32_t*      outNodes)
+{
+    BatchIO       io{{cursor, numRays}, rays, tris, rayTMax, outHit, outPT, outNodes};
+    std::uint32_t records = 0;
+    traceRaysPairs<0, PAIR_DEFAULT_VARIANT, TRACE_BLOCK_THREADS>(pairs, tris, ordered, tuning, io, records);
 }
 } // namespace rfb200

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_mega(
     {
         const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};
         atomicAdd(&stats[slot[threadIdx.x]], static_cast<unsigned long long>(sh.blockStats[threadIdx.x]));
+        if (threadIdx.x == 1 || threadIdx.x == 4) atomicAdd(&stats[STAT_RECORDS], static_cast<unsigned long long>(sh.blockStats[threadIdx.x]));
     }
 }
 } // namespace rfb200

@@ -48,19 +48,24 @@ def test_config1_sponza_1080p_1spp_8_bounces_matches_oracle(sponza_pt):
     err = O.rmse(img, orc.image)
     assert err < RMSE_TOLERANCE, err
     assert np.isfinite(img).all() and np.all(img[..., 3] == 0)
-    default_schedule = (stats["sub_frames"], stats["evict_max"])
+    assert stats["trace_kernel"] == 2  # Sponza's leaves fit the child-pair records: that kernel is the default
 
-    # the same frame under every other schedule: never a counter or a pixel changes
-    schedules = {"one tile set, rays end in place": (1, 0, 0), "one tile set + tail hand-over": (1, 0, 8),
-                 "two tile sets + tail hand-over": (2, 0, 32), "persistent kernel": (1, 1, 0), "persistent kernel, two tile sets": (2, 1, 0)}
-    for name, (sub_frames, persistent, evict_max) in schedules.items():
+    # the same frame under every other kernel and schedule: never a counter or a pixel changes
+    schedules = {  # name: (trace kernel, pair variant, tile sets, persistent kernel, tail hand-over)
+        "pairs, definite misses not pushed, one tile set": (2, 7, 1, 0, 0), "pairs, 2 steps per vote, two tile sets": (2, 1, 2, 0, 0),
+        "per-node kernel, rays end in place": (1, 0, 1, 0, 0), "per-node kernel + tail hand-over": (1, 0, 1, 0, 8),
+        "per-node kernel, two tile sets + tail hand-over": (1, 0, 2, 0, 32), "persistent kernel": (1, 0, 1, 1, 0),
+        "persistent kernel, two tile sets": (1, 0, 2, 1, 0)}
+    for name, (kernel, pair_variant, sub_frames, persistent, evict_max) in schedules.items():
         other, _ = make_renderer(sponza_pt, w, h, 1, bounces)
+        other.set_option("trace_kernel", kernel)
+        other.set_option("pair_variant", pair_variant)
         other.set_pipeline(sub_frames, persistent, -1, 0)
         other.set_tail_policy(evict_max)
         other.render()
         img2, _ = other.read_hdr()
         s2 = other.stats()
-        assert (s2["sub_frames"], s2["evict_max"]) != default_schedule or persistent, name
+        assert s2["trace_kernel"] == kernel and s2["sub_frames"] == sub_frames and s2["evict_max"] == evict_max, name
         for key in O.COUNTER_NAMES:
             assert s2[key] == stats[key], (name, key)
         assert np.array_equal(img2.view(np.uint32), img.view(np.uint32)), name

@@ -304,29 +304,43 @@ def test_texture_limit_error_message(duck_pt):
     assert str(e.value) == f"Texture buffer size ({huge.size * 4}) exceeds maxStorageBufferBindingSize ({1 << 30})."
 
 
-@pytest.mark.parametrize("sub_frames,persistent,variant,block,tri_min,refill_min,evict_max", [
-    (1, 0, 3, 256, 4, 4, 0), (2, 0, 3, 256, 4, 4, -1), (4, 0, 2, 64, 1, 1, 8), (3, 0, 1, 128, 32, 32, 32), (1, 0, 11, 256, 8, 16, 1),
-    (1, 0, 3, 256, 4, 4, 32), (2, 0, 3, 256, 4, 4, 0), (1, 1, 3, 256, 4, 4, -1), (2, 1, 3, 128, 2, 8, -1)])
-def test_results_do_not_depend_on_scheduling(duck_pt, sub_frames, persistent, variant, block, tri_min, refill_min, evict_max):
-    """Sub-frame pipelining, the experimental persistent kernel, the compile-time scheduling variants, block sizes,
-    the run-time knobs and the straggler hand-over (rays moved to another lane in mid-traversal) change how warps are
-    kept busy — never a counter or a pixel."""
+@pytest.mark.parametrize("kernel,sub_frames,persistent,variant,block,tri_min,refill_min,evict_max", [
+    (1, 1, 0, 3, 256, 4, 4, 0), (1, 2, 0, 3, 256, 4, 4, -1), (1, 4, 0, 2, 64, 1, 1, 8), (1, 3, 0, 1, 128, 32, 32, 32), (1, 1, 0, 11, 256, 8, 16, 1),
+    (1, 1, 0, 3, 256, 4, 4, 32), (1, 2, 0, 3, 256, 4, 4, 0), (1, 1, 1, 3, 256, 4, 4, -1), (1, 2, 1, 3, 128, 2, 8, -1),
+    (2, 1, 0, 3, 256, 4, 4, 0), (2, 2, 0, 7, 256, 4, 4, 0), (2, 3, 0, 1, 256, 1, 1, 0), (2, 1, 0, 5, 256, 32, 32, 0), (2, 4, 0, 7, 256, 8, 2, 0)])
+def test_results_do_not_depend_on_scheduling(duck_pt, kernel, sub_frames, persistent, variant, block, tri_min, refill_min, evict_max):
+    """The traversal kernel (child-pair records or one node per visit), sub-frame pipelining, the experimental persistent
+    kernel, the compile-time scheduling variants, block sizes, the run-time knobs and the straggler hand-over (rays moved to
+    another lane in mid-traversal) change how warps are kept busy — never a counter or a pixel."""
     w, h, spp, bounces = 150, 70, 2, 5
     cam = rf.bvh_visualizer_camera(duck_pt.bvh_nodes, w, h)
     ren, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
+    ren.set_option("trace_kernel", 1)
     ren.set_pipeline(1, 0, 3, 256)
     ren.set_tail_policy(0)
     ren.render(), ren.render()
     ref_img, _ = ren.read_hdr()
     ref_stats = ren.stats()
+    assert ref_stats["trace_kernel"] == 1 and ref_stats["node_records_loaded"] == ref_stats["closest_nodes_visited"] + ref_stats["shadow_nodes_visited"]
     ren2, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
+    ren2.set_option("trace_kernel", kernel)
     ren2.set_tuning(tri_min, refill_min, 4)
-    ren2.set_pipeline(sub_frames, persistent, variant, block)
+    if kernel == 2:
+        ren2.set_option("pair_variant", variant)
+        ren2.set_pipeline(sub_frames, persistent, -1, 0)
+    else:
+        ren2.set_pipeline(sub_frames, persistent, variant, block)
     ren2.set_tail_policy(evict_max)
     ren2.render(), ren2.render()
     img, _ = ren2.read_hdr()
+    stats = ren2.stats()
+    assert stats["trace_kernel"] == (1 if persistent else kernel)
+    if kernel == 2:  # every record decides two visits; a ray that ends early leaves pushed entries unvisited
+        visits = stats["closest_nodes_visited"] + stats["shadow_nodes_visited"]
+        rays = stats["closest_rays"] + stats["shadow_rays"]
+        assert (stats["closest_nodes_visited"] - stats["closest_rays"]) // 2 <= stats["node_records_loaded"] <= visits - rays
     for key in O.COUNTER_NAMES:
-        assert ren2.stats()[key] == ref_stats[key], key
+        assert stats[key] == ref_stats[key], key
     assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
 
 
@@ -340,6 +354,7 @@ def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames):
     w, h, bounces = 480, 270, 8
     cam = rf.fly_camera(w, h)
     ren, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+    ren.set_option("trace_kernel", 1)  # the tail hand-over belongs to the one-node-per-visit kernel
     ren.set_pipeline(1, 0, 3, 256)
     ren.set_tail_policy(0)
     ren.render(), ren.render()
@@ -347,6 +362,7 @@ def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames):
     ref_stats = ren.stats()
     assert ref_stats["evict_max"] == 0 and ref_stats["sub_frames"] == 1
     ren2, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+    ren2.set_option("trace_kernel", 1)
     ren2.set_pipeline(sub_frames, 0, 3, 256)
     ren2.set_tail_policy(evict_max)
     ren2.render(), ren2.render()
