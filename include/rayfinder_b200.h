@@ -273,13 +273,15 @@ rf_status rf_renderer_reset_stats(rf_renderer* r);
 rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled);
 /* Scheduling knobs of the persistent traversal kernels (results never depend on them): a triangle round
  * runs once `tri_min` lanes of a warp have a triangle pending, idle lanes are refilled once `refill_min`
- * are idle, `blocks_per_sm` persistent 256-thread blocks are launched per SM.  0 keeps a value. */
+ * are idle, `blocks_per_sm` persistent 256-thread blocks are launched per SM (automatic until set: 4, or 2 per tile set
+ * for a small frame, see rf_renderer_set_pipeline).  0 keeps a value. */
 rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refill_min, uint32_t blocks_per_sm);
-/* How a frame is scheduled (results never depend on it).  sub_frames (1..4, 0 keeps, -1 automatic = the default:
- * 2 above ~0.6 M owned pixels, else 1): the frame is traced as that many independent tile sets on separate CUDA
- * streams so one set's traversal tail overlaps the other's work.  persistent_kernel (0/1, -1 keeps): experimental single-launch pipeline (csrc/mega.cuh) instead of one
- * launch per stage.  variant (0..15, -1 keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling
- * variant and block size of the traversal kernel. */
+/* How a frame is scheduled (results never depend on it).  sub_frames (1..4, 0 keeps, -1 automatic = the default: 2):
+ * the frame is traced as that many independent tile sets on separate CUDA streams so one set's traversal tail overlaps
+ * the other's work; when this GPU owns at most ~0.6 M pixels the automatic schedule also gives each set's traversal
+ * launches half of the SM slots (both sets resident together) and turns the tail hand-over on.  persistent_kernel (0/1,
+ * -1 keeps): experimental single-launch pipeline (csrc/mega.cuh) instead of one launch per stage.  variant (0..15, -1
+ * keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling variant and block size of the traversal kernel. */
 rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t persistent_kernel, int32_t variant, int32_t block_threads);
 /* Tail policy of the traversal launches (results never depend on it).  Once a launch's ray queue is dry, a warp left
  * with <= evict_max rays keeps them for four more loop rounds (most of them are short and end there), then writes the
@@ -292,6 +294,10 @@ rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
  *   "shade_wait"   persistent kernel: 0.5 us naps its shading warp takes to let a batch of 32 hits fill (default 16)
  *   "evict_delay"  loop rounds a warp keeps its last rays before handing them to the tail launch (default 4)
  *   "trace_stack"  force at least this many traversal-stack entries (<= 32; 0 = what the scene needs, the default)
+ *   "trace_kernel" 0 / 1: traversal over 32-byte nodes, one per visit (csrc/traversal.cuh; the default); 2: over 64-byte
+ *                  child-pair records, one per interior node entered (csrc/traversal_pairs.cuh)
+ *   "pair_variant" scheduling variant of the child-pair kernel: bits 0-1 = rounds per warp vote - 1, bit 2 = closest-hit rays
+ *                  do not push far children that miss whatever tmax is (1, 3, 5 or 7)
  *   "stage_debug"  1: print the per-launch spans of every stage-timed frame to stderr
  *   "mega_debug"   1: print the persistent kernel's control block after every frame (synchronises) */
 rf_status rf_renderer_set_option(rf_renderer* r, const char* name, int64_t value);
@@ -340,6 +346,10 @@ rf_status rf_traversal_scene_create(
     int32_t              device,
     rf_traversal_scene** out);
 void rf_traversal_scene_destroy(rf_traversal_scene* s);
+/* Traversal kernel of the calls below (results never depend on it): 0 / 1 = one 32-byte node per visit (the default),
+ * 2 = one 64-byte child-pair record per interior node entered (csrc/traversal_pairs.cuh; scenes whose leaves do not fit
+ * its links keep the per-node kernel).  The renderer's counterpart is rf_renderer_set_option("trace_kernel", ...). */
+rf_status rf_traversal_scene_set_kernel(rf_traversal_scene* s, int32_t trace_kernel);
 
 /* Batched rayIntersectBvh (ray_intersection.cpp:138-213) on host buffers.  rays: n x 6 floats
  * (origin, direction).  Outputs (each may be NULL): out_hit n x u8 (the bool result); out_p_t n x 4

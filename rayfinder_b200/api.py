@@ -438,6 +438,10 @@ class TraversalScene:
 
     __del__ = close
 
+    def set_kernel(self, trace_kernel: int) -> None:
+        """0 / 1: one node per visit (default); 2: child-pair records."""
+        check(lib().rf_traversal_scene_set_kernel(self._handle, trace_kernel))
+
     def ray_intersect_bvh(self, rays: np.ndarray, ray_t_max: float):
         """rays (n, 6) -> (hit bool[n], p_t float32[n, 4], nodes_visited uint32[n])."""
         rays = np.ascontiguousarray(rays, dtype="<f4").reshape(-1, 6)

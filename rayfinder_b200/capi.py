@@ -125,6 +125,7 @@ SIGNATURES = {
     "rf_renderer_read_deferred": (C.c_int32, [_P, _P, _P, _P]),
     "rf_traversal_scene_create": (C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(_P)]),
     "rf_traversal_scene_destroy": (None, [_P]),
+    "rf_traversal_scene_set_kernel": (C.c_int32, [_P, C.c_int32]),
     "rf_ray_intersect_bvh": (C.c_int32, [_P, _P, C.c_uint64, C.c_float, _P, _P, _P]),
     "rf_bvh_visualizer_node_counts": (C.c_int32, [_P, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_float, _P, C.POINTER(C.c_float)]),
     "rf_pick_focus_distance": (C.c_int32, [_P, C.POINTER(Camera), C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_double, C.c_double,

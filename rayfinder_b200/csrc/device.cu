@@ -257,9 +257,11 @@ struct rf_renderer
     TraceTuning                 tuning = defaultTuning();
     DeviceBuffer<PairRecord>    pairRecords;  // child-pair records (pair_records.h); empty when the scene's leaves do not fit a link
     PairSceneDevice             pairsDev{};
-    int                         traceKernel = 0;  // 0: automatic (pairs when the scene has them), 1: one node per visit, 2: pairs
+    // 0 / 1: one node per visit (traversal.cuh, the default: measured faster, DESIGN.md "Child-pair records"), 2: child-pair
+    // records (traversal_pairs.cuh) when the scene has them
+    int                         traceKernel = 0;
     int                         pairVariant = PAIR_DEFAULT_VARIANT;
-    bool                        usePairs() const { return pairsDev.records != nullptr && traceKernel != 1; }
+    bool                        usePairs() const { return pairsDev.records != nullptr && traceKernel == 2; }
     DeviceBuffer<uint4>         texDesc;
     DeviceBuffer<std::uint32_t> texels;
     DeviceBuffer<uchar2>        blueNoise;
@@ -459,7 +461,7 @@ struct rf_renderer
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) ++ownedTileCount;
-        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : (smallFrame() ? 1 : 2);
+        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : 2;
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) owned[k++ % static_cast<std::uint32_t>(numSubFrames)].push_back(ty * tilesX + tx);
@@ -498,15 +500,20 @@ struct rf_renderer
     }
 
     int variant = TRACE_DEFAULT_VARIANT; // scheduling variant of the traversal kernels (traversal.cuh)
-    int traceBlocksPerSm = 4; // in units of 256 threads: x <= 64 registers, 32 KB of shared stack
+    int traceBlocksPerSm = 0; // persistent traversal blocks per SM in units of 256 threads (0: automatic; 4 fill an SM: <= 64 registers, 32 KB stack)
+    // Automatic: a launch of a full frame fills the machine (4); the launches of a small frame's two tile sets take half of it
+    // each (2), so that both sets' kernels are resident together and one set's tail overlaps the other's steady state
+    // (measured at 672x384 / 960x540, the shares of 8 / 4 GPUs: 3.15 / 5.04 ms against 3.27 / 5.24 ms with one set on 4).
+    int effectiveBlocksPerSm() const { return traceBlocksPerSm > 0 ? traceBlocksPerSm : (smallFrame() && numSubFrames == 2 ? 2 : 4); }
     int traceBlock = 256;     // threads per traversal block (64, 128 or 256)
     int gridFor(int blocksPerSm) const { return numSms * blocksPerSm; }
     // Tail policy of the traversal launches: warps left with <= evictMax rays once the queue is dry hand them to a
     // small follow-up launch (0 = off).  On by default when the frame runs as several tile sets, where the SMs a
     // tail frees are used by the other sets.
-    // Automatic scheduling, from measurements on B200 (Sponza, 8 bounces; DESIGN.md "Tails"): with more than ~0.6 M
-    // paths per GPU (the 1080p frame on 1-2 GPUs) two tile sets on two streams and no hand-over are fastest; below
-    // that (a 1080p frame split over 4-8 GPUs) a launch is mostly tail and one tile set with the hand-over wins.
+    // Automatic scheduling, from measurements on B200 (Sponza, 8 bounces; DESIGN.md "Tails"): a frame is always traced as
+    // two tile sets on two streams.  With more than ~0.6 M paths per GPU (the 1080p frame on 1-2 GPUs) every traversal launch
+    // fills the machine and ends its rays in place; below that (a 1080p frame split over 4-8 GPUs) a launch is mostly tail:
+    // each set's launches take half the SM slots, so both sets are resident together, and hand their tails over.
     std::uint32_t stackEntries = RF_STACK_SIZE; // deepest traversal stack the scene can produce (validateBvh)
     // option "trace_stack" = 32 forces the reference-sized stack (A/B runs)
     std::uint32_t forcedStackEntries = 0;
@@ -583,7 +590,7 @@ extern "C" rf_status rf_renderer_create(
         // + 64 zeroed records: the tail kernel reads 32-node windows that may run past the last node (straggler.cuh)
         RF_CUDA(r->nodes.allocate(numNodes + 64));
         RF_CUDA(cudaMemset(r->nodes.ptr, 0, (numNodes + 64) * sizeof(PackedNode)));
-        RF_CUDA(r->tris.allocate(3 * numTris));
+        RF_CUDA(r->tris.allocate(TRI_STRIDE * numTris));
         k_pack_nodes<<<r->numSms * 4, 256>>>(rawNodes.ptr, numNodes, r->nodes.ptr);
         k_pack_triangles<<<r->numSms * 4, 256>>>(rawTris.ptr, 4, numTris, r->tris.ptr);
         RF_CUDA(cudaGetLastError());
@@ -739,7 +746,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     RF_CUDA(cudaEventRecord(r->forkEvent, s));
 
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->traceBlocksPerSm) : r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
+    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->effectiveBlocksPerSm()) : r->gridFor(r->effectiveBlocksPerSm() * (256 / r->traceBlock));
     RF_CUDA(stageMark());
     for (int i = 0; i < r->numSubFrames; ++i)
     {
@@ -933,7 +940,7 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     std::uint32_t* const cursors = ctr + 2;
     const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u, 0u};
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->traceBlocksPerSm) : r->gridFor(r->traceBlocksPerSm * (256 / r->traceBlock));
+    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->effectiveBlocksPerSm()) : r->gridFor(r->effectiveBlocksPerSm() * (256 / r->traceBlock));
     RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(1) * sizeof(std::uint32_t), s));
     k_deferred_primary<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, un, d.albedo.ptr, d.normal.ptr, d.depth.ptr, queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
     // shadow rays of the G-buffer surfaces + the bounce rays
@@ -1244,6 +1251,8 @@ struct rf_traversal_scene
     std::uint64_t               numNodes = 0, numTris = 0;
     DeviceBuffer<PairRecord>    pairRecords; // child-pair records (pair_records.h) when the scene's leaves fit a link
     PairSceneDevice             pairsDev{};
+    int                         traceKernel = 0; // as rf_renderer's: 2 selects the child-pair kernel
+    bool                        usePairs() const { return pairsDev.records != nullptr && traceKernel == 2; }
 };
 
 extern "C" rf_status rf_traversal_scene_create(
@@ -1270,7 +1279,7 @@ extern "C" rf_status rf_traversal_scene_create(
     RF_CUDA(cudaMemcpy(rawTris.ptr, triangles, numTriangles * sizeof(rf_positions), cudaMemcpyHostToDevice));
     RF_CUDA(s->nodes.allocate(numNodes));
     RF_CUDA(s->cursor.allocate(1));
-    RF_CUDA(s->tris.allocate(3 * numTriangles));
+    RF_CUDA(s->tris.allocate(TRI_STRIDE * numTriangles));
     k_pack_nodes<<<s->numSms * 4, 256>>>(rawNodes.ptr, numNodes, s->nodes.ptr);
     k_pack_triangles<<<s->numSms * 4, 256>>>(rawTris.ptr, 3, numTriangles, s->tris.ptr);
     RF_CUDA(cudaGetLastError());
@@ -1287,6 +1296,13 @@ extern "C" rf_status rf_traversal_scene_create(
         s->pairsDev.rootLink = ps.rootLink;
     }
     *out = s.release();
+    return RF_OK;
+}
+
+extern "C" rf_status rf_traversal_scene_set_kernel(rf_traversal_scene* s, std::int32_t traceKernel)
+{
+    if (!s || traceKernel < 0 || traceKernel > 2) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_traversal_scene_set_kernel: bad argument");
+    s->traceKernel = traceKernel;
     return RF_OK;
 }
 
@@ -1321,7 +1337,7 @@ extern "C" rf_status rf_ray_intersect_bvh(
     const std::uint64_t blocksNeeded = (numRays + TRACE_BLOCK_THREADS - 1) / TRACE_BLOCK_THREADS;
     const int           grid = static_cast<int>(std::min<std::uint64_t>(blocksNeeded, static_cast<std::uint64_t>(s->numSms) * 4));
     RF_CUDA(cudaMemset(s->cursor.ptr, 0, sizeof(std::uint32_t)));
-    if (s->pairsDev.records)
+    if (s->usePairs())
         k_intersect_batch_pairs<<<grid, TRACE_BLOCK_THREADS>>>(
             s->pairsDev, s->tris.ptr, s->ordered, s->tuning, dRays.ptr, static_cast<std::uint32_t>(numRays), rayTMax, s->cursor.ptr, dHit.ptr, dPT.ptr,
             dNodes.ptr);
@@ -1388,7 +1404,7 @@ extern "C" rf_status rf_bvh_visualizer_node_counts(
     RF_CUDA(cudaEventCreate(&e1));
     RF_CUDA(cudaMemset(s->cursor.ptr, 0, sizeof(std::uint32_t)));
     RF_CUDA(cudaEventRecord(e0));
-    if (s->pairsDev.records)
+    if (s->usePairs())
         k_visualizer_pairs<<<s->numSms * 4, TRACE_BLOCK_THREADS>>>(
             s->pairsDev, s->tris.ptr, s->ordered, s->tuning, *camera, width, height, rayTMax, s->cursor.ptr, dNodes.ptr);
     else

@@ -53,7 +53,7 @@ struct FrameParams
 struct SceneDevice
 {
     const PackedNode*    nodes;      // 32 B per node
-    const float4*        tris;       // 3 x float4 per triangle
+    const float4*        tris;       // TRI_STRIDE x float4 per triangle
     const float4*        vattr;      // 5 x float4 per triangle (VertexAttributes as-is)
     const uint4*         texDesc;    // (width, height, offset, 0)
     const std::uint32_t* texels;     // BGRA8
@@ -648,9 +648,10 @@ __global__ void k_pack_triangles(const float* __restrict__ src, const int stride
         const V3     v0 = v3(t), v1 = v3(t + strideFloats), v2 = v3(t + 2 * strideFloats);
         const V3     e1 = v1 - v0, e2 = v2 - v0;
         const V3     nrm = normalize(cross(e1, e2)); // wgsl:513 / ray_intersection.cpp:80
-        dst[3 * i + 0] = make_float4(v0.x, v0.y, v0.z, e1.x);
-        dst[3 * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
-        dst[3 * i + 2] = make_float4(e2.z, nrm.x, nrm.y, nrm.z);
+        dst[TRI_STRIDE * i + 0] = make_float4(v0.x, v0.y, v0.z, e1.x);
+        dst[TRI_STRIDE * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+        dst[TRI_STRIDE * i + 2] = make_float4(e2.z, nrm.x, nrm.y, nrm.z);
+        dst[TRI_STRIDE * i + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 

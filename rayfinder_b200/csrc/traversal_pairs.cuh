@@ -92,10 +92,18 @@ __device__ __forceinline__ float slabEntry(
 }
 
 // The persistent traversal loop over pair records.  IO as for traceRays (acquire / fetch / finish); MODE 0 closest hit,
-// 1 any-hit, 2 per ray.  VARIANT bits 0-1: steps per warp vote minus 1; bit 2: closest-hit rays do not push far children
+// 1 any-hit, 2 per ray.  VARIANT bits 0-1: rounds per warp vote minus 1; bit 2: closest-hit rays do not push far children
 // whose box is missed whatever tmax is (their visit is counted at once: every pushed entry of a closest-hit ray is popped
 // eventually, so the total is the reference's; an any-hit ray may stop early and must count each visit when it happens).
-constexpr int PAIR_DEFAULT_VARIANT = 3;
+//
+// SIMT shape of a round (what the lanes of a warp execute together):
+//   pops     a short divergent loop: every lane that needs an entry pops until one is entered (two shared-memory reads and a
+//            compare per pop — a popped entry that misses costs nothing else);
+//   expand   straight-line, predicated: every lane that entered an interior node loads its record, runs both slab tests,
+//            pushes the far child and steps to the near one.
+// Keeping the expensive part convergent is what the split buys: in a first version with one pop and one expand per lane per
+// round the warps ran at 14-15 of 32 lanes per instruction (profiles/r02_pairs_v1_ncu.txt).
+constexpr int PAIR_DEFAULT_VARIANT = 5;
 template<int MODE, int VARIANT, int BLOCK, class IO>
 __device__ __forceinline__ void traceRaysPairs(
     const PairSceneDevice& pairs,
@@ -118,51 +126,30 @@ __device__ __forceinline__ void traceRaysPairs(
     {
         IDLE = 0,   // no ray
         EXPAND = 1, // next action: load record `cur`, visit its near child, push its far child
-        TRI = 2,    // parked at a leaf: triangles [pendTri, pendEnd) to test
+        TRI = 2,    // parked at the leaf `cur` (a leaf link): its triangles from number `triDone` on are still to test
         DONE = 3,   // traversal finished, result not yet handed to IO
         POP = 4     // next action: pop an entry and complete its slab test
     };
-    constexpr int  STEPS_PER_VOTE = (VARIANT & 3) + 1;
+    constexpr int  ROUNDS_PER_VOTE = (VARIANT & 3) + 1;
     constexpr bool SKIP_DEFINITE_MISSES = (VARIANT & 4) != 0;
+    const float    INF = __int_as_float(0x7F800000);
 
     int           state = IDLE;
     std::uint32_t rayIdx = 0;
     V3            o = v3(0.f, 0.f, 0.f), d = o;
     float         ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
     std::uint32_t negMask = 0; // bit a = invDir[a] < 0 (dirNeg); bit 3 = literal slab test for every box of this ray
-    std::uint32_t cur = 0, pendTri = 0, pendEnd = 0, rayNodes = 0, rayTris = 0;
+    std::uint32_t cur = 0;     // EXPAND: record index; TRI: the leaf's link
+    std::uint32_t triDone = 0, rayNodes = 0, rayTris = 0;
     HitRecord     hit{RF_NO_HIT, 0.f, 0.f, 0.f};
     bool          exhausted = false;
     bool          laneAnyHit = false;
 #define RF_ANY_HIT (MODE == 2 ? laneAnyHit : (MODE == 1))
 
-    // Where `link` leads once its box is known to be entered.
+    // Where `link` leads once its box is known to be entered: EXPAND for a record index, TRI for a leaf link (bit 31).
     const auto enter = [&](const std::uint32_t link) {
-        if (link & PAIR_LINK_LEAF)
-        {
-            pendTri = link & 0xFFFFFFu;
-            pendEnd = pendTri + ((link >> 24) & 127u) + 1u;
-            state = TRI;
-        }
-        else
-        {
-            cur = link;
-            state = EXPAND;
-        }
-    };
-
-    const auto push = [&](const std::uint32_t link, const float t) {
-        if (stackTop < stackLimit)
-        {
-            stackStore(stackTop, link);
-            stackStore(stackTop + WORD_STRIDE, __float_as_uint(t));
-        }
-        else
-        {
-            const std::uint32_t k = (stackTop - stackLimit) / ENTRY_STRIDE;
-            deepLink[k] = link, deepT[k] = t;
-        }
-        stackTop += ENTRY_STRIDE;
+        cur = link;
+        state = EXPAND + static_cast<int>(link >> 31);
     };
 
     // One pop (ray_intersection.cpp:200-203 followed by the next iteration's :158-160): the entry's visit is counted, its
@@ -176,15 +163,15 @@ __device__ __forceinline__ void traceRaysPairs(
         stackTop -= ENTRY_STRIDE;
         std::uint32_t link;
         float         t;
-        if (stackTop < stackLimit)
-        {
-            link = stackLoad(stackTop);
-            t = __uint_as_float(stackLoad(stackTop + WORD_STRIDE));
-        }
-        else
+        if (__builtin_expect(stackTop >= stackLimit, 0))
         {
             const std::uint32_t k = (stackTop - stackLimit) / ENTRY_STRIDE;
             link = deepLink[k], t = deepT[k];
+        }
+        else
+        {
+            link = stackLoad(stackTop);
+            t = __uint_as_float(stackLoad(stackTop + WORD_STRIDE));
         }
         ++rayNodes;
         if (t < tmax) enter(link); // else: missed, stay in POP
@@ -194,18 +181,48 @@ __device__ __forceinline__ void traceRaysPairs(
     const auto expandStep = [&]() {
         ++recordsLoaded;
         const PairHalves r = loadPair(pairs.records + cur);
-        const bool       exact = (negMask & 8u) != 0u;
-        const float      t0 = slabEntry(r.a[0], r.a[1], r.a[2], r.a[3], r.a[4], r.a[5], negMask, o, ix, iy, iz, exact);
-        const float      t1 = slabEntry(r.a[6], r.a[7], r.b[0], r.b[1], r.b[2], r.b[3], negMask, o, ix, iy, iz, exact);
+        // fast form of both slab tests (traversal.cuh, DESIGN.md "Slab test"), split at the tmax-dependent term
+        const float ax0 = (r.a[0] - o.x) * ix, ax1 = (r.a[3] - o.x) * ix;
+        const float ay0 = (r.a[1] - o.y) * iy, ay1 = (r.a[4] - o.y) * iy;
+        const float az0 = (r.a[2] - o.z) * iz, az1 = (r.a[5] - o.z) * iz;
+        const float bx0 = (r.a[6] - o.x) * ix, bx1 = (r.b[1] - o.x) * ix;
+        const float by0 = (r.a[7] - o.y) * iy, by1 = (r.b[2] - o.y) * iy;
+        const float bz0 = (r.b[0] - o.z) * iz, bz1 = (r.b[3] - o.z) * iz;
+        const float aMin = max3Nan(minNan(ax0, ax1), minNan(ay0, ay1), minNan(az0, az1));
+        const float aMax = min3Nan(maxNan(ax0, ax1), maxNan(ay0, ay1), maxNan(az0, az1));
+        const float bMin = max3Nan(minNan(bx0, bx1), minNan(by0, by1), minNan(bz0, bz1));
+        const float bMax = min3Nan(maxNan(bx0, bx1), maxNan(by0, by1), maxNan(bz0, bz1));
+        float       t0 = ((aMin <= aMax) && (aMax > 0.0f)) ? aMin : INF;
+        float       t1 = ((bMin <= bMax) && (bMax > 0.0f)) ? bMin : INF;
+        if (__builtin_expect((negMask & 8u) != 0u || eitherNan(aMin, aMax) || eitherNan(bMin, bMax), 0))
+        {
+            // a NaN slab product (0 * inf), or a ray / scene that needs the literal form throughout
+            t0 = slabEntryExact(r.a[0], r.a[1], r.a[2], r.a[3], r.a[4], r.a[5], negMask, o, ix, iy, iz);
+            t1 = slabEntryExact(r.a[6], r.a[7], r.b[0], r.b[1], r.b[2], r.b[3], negMask, o, ix, iy, iz);
+        }
         // near child first by the sign of invDir[splitAxis] (ray_intersection.cpp:184-199); the other one is pushed
         const bool          nearIsSecond = ((negMask >> (r.meta & 3u)) & 1u) != 0u;
         const float         tNear = nearIsSecond ? t1 : t0, tFar = nearIsSecond ? t0 : t1;
         const std::uint32_t linkNear = nearIsSecond ? r.link1 : r.link0, linkFar = nearIsSecond ? r.link0 : r.link1;
-        if (SKIP_DEFINITE_MISSES && !RF_ANY_HIT && tFar == __int_as_float(0x7F800000))
-            ++rayNodes; // the far child's visit will miss whatever happens: count it now, push nothing
+        rayNodes += 1; // the near child's visit
+        if (SKIP_DEFINITE_MISSES && !RF_ANY_HIT && tFar == INF)
+        {
+            rayNodes += 1; // the far child's visit will miss whatever happens: count it now, push nothing
+        }
         else
-            push(linkFar, tFar);
-        ++rayNodes; // the near child's visit
+        {
+            if (__builtin_expect(stackTop >= stackLimit, 0))
+            {
+                const std::uint32_t k = (stackTop - stackLimit) / ENTRY_STRIDE;
+                deepLink[k] = linkFar, deepT[k] = tFar;
+            }
+            else
+            {
+                stackStore(stackTop, linkFar);
+                stackStore(stackTop + WORD_STRIDE, __float_as_uint(tFar));
+            }
+            stackTop += ENTRY_STRIDE;
+        }
         if (tNear < tmax)
             enter(linkNear);
         else
@@ -222,7 +239,7 @@ __device__ __forceinline__ void traceRaysPairs(
         const bool exact = !sceneOrdered || !(ix == ix && iy == iy && iz == iz && ix != 0.0f && iy != 0.0f && iz != 0.0f &&
                                               isFiniteBits(o.x) && isFiniteBits(o.y) && isFiniteBits(o.z));
         if (exact) negMask |= 8u;
-        rayNodes = 1, rayTris = 0;
+        rayNodes = 1, rayTris = 0, triDone = 0;
         stackTop = stackBase;
         hit.tri = RF_NO_HIT;
         const float t = slabEntry(pairs.rootBox[0], pairs.rootBox[1], pairs.rootBox[2], pairs.rootBox[3], pairs.rootBox[4], pairs.rootBox[5], negMask, o,
@@ -235,11 +252,11 @@ __device__ __forceinline__ void traceRaysPairs(
 
     while (true)
     {
-        // ---- node steps ---------------------------------------------------------------------------------
+        // ---- node rounds ----------------------------------------------------------------------------------
 #pragma unroll
-        for (int k = 0; k < STEPS_PER_VOTE; ++k)
+        for (int k = 0; k < ROUNDS_PER_VOTE; ++k)
         {
-            if (state == POP) popStep();
+            while (state == POP) popStep();
             if (state == EXPAND) expandStep();
         }
 
@@ -251,24 +268,26 @@ __device__ __forceinline__ void traceRaysPairs(
         {
             if (state == TRI)
             {
+                const std::uint32_t tri = (cur & 0xFFFFFFu) + triDone;
                 ++rayTris;
+                ++triDone;
                 float u, v, t;
                 bool  done = false;
-                if (intersectTriangle(tris, pendTri, o, d, tmax, u, v, t))
+                if (intersectTriangle(tris, tri, o, d, tmax, u, v, t))
                 {
-                    hit.tri = pendTri, hit.u = u, hit.v = v, hit.t = t;
+                    hit.tri = tri, hit.u = u, hit.v = v, hit.t = t;
                     if (RF_ANY_HIT)
                         done = true; // shadowRay returns on the first accepted triangle (wgsl:340-342)
                     else
                         tmax = t;
                 }
-                ++pendTri;
-                if (done)
-                    state = DONE;
-                else if (pendTri == pendEnd)
-                    state = POP;
+                if (done || triDone == ((cur >> 24) & 127u) + 1u)
+                {
+                    triDone = 0;
+                    state = done ? DONE : POP;
+                }
             }
-            continue; // the masks are stale now; vote again after the next node steps
+            continue; // the masks are stale now; vote again after the next node rounds
         }
 
         // ---- hand finished rays to IO, refill idle lanes with the next work items, terminate ----------

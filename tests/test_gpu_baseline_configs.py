@@ -48,12 +48,12 @@ def test_config1_sponza_1080p_1spp_8_bounces_matches_oracle(sponza_pt):
     err = O.rmse(img, orc.image)
     assert err < RMSE_TOLERANCE, err
     assert np.isfinite(img).all() and np.all(img[..., 3] == 0)
-    assert stats["trace_kernel"] == 2  # Sponza's leaves fit the child-pair records: that kernel is the default
+    assert stats["trace_kernel"] == 1  # the default: one node per visit
 
     # the same frame under every other kernel and schedule: never a counter or a pixel changes
     schedules = {  # name: (trace kernel, pair variant, tile sets, persistent kernel, tail hand-over)
-        "pairs, definite misses not pushed, one tile set": (2, 7, 1, 0, 0), "pairs, 2 steps per vote, two tile sets": (2, 1, 2, 0, 0),
-        "per-node kernel, rays end in place": (1, 0, 1, 0, 0), "per-node kernel + tail hand-over": (1, 0, 1, 0, 8),
+        "child-pair records, one tile set": (2, 7, 1, 0, 0), "child-pair records, every far child pushed, two tile sets": (2, 1, 2, 0, 0),
+        "per-node kernel, one tile set, rays end in place": (1, 0, 1, 0, 0), "per-node kernel + tail hand-over": (1, 0, 1, 0, 8),
         "per-node kernel, two tile sets + tail hand-over": (1, 0, 2, 0, 32), "persistent kernel": (1, 0, 1, 1, 0),
         "persistent kernel, two tile sets": (1, 0, 2, 1, 0)}
     for name, (kernel, pair_variant, sub_frames, persistent, evict_max) in schedules.items():

@@ -28,9 +28,11 @@ def assert_counters_equal(gpu_stats, oracle_stats):
 
 
 # ---- config 1: node-count image ------------------------------------------------------------------------
-def test_duck_node_counts_bit_exact(duck_pt, golden):
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_duck_node_counts_bit_exact(duck_pt, golden, kernel):
     g = golden["ref_duck_node_counts"]
     scene = rf.TraversalScene(duck_pt.bvh_nodes, O.triangles9(duck_pt))
+    scene.set_kernel(kernel)
     for (w, h) in ((512, 512), (1280, 720)):
         cam = rf.bvh_visualizer_camera(duck_pt.bvh_nodes, w, h)
         assert np.array_equal(rf.camera_to_array(cam).view(np.uint32), g[f"camera_{w}x{h}"].view(np.uint32))
@@ -46,7 +48,7 @@ def test_duck_node_counts_bit_exact(duck_pt, golden):
 
 
 def test_sponza_node_counts_bit_exact(sponza_pt):
-    """Interior benchmark camera, full 1080p: every per-pixel count equals the oracle's."""
+    """Interior benchmark camera, full 1080p: every per-pixel count equals the oracle's, with either traversal kernel."""
     w, h = 1920, 1080
     tris = O.triangles9(sponza_pt)
     scene = rf.TraversalScene(sponza_pt.bvh_nodes, tris)
@@ -54,14 +56,19 @@ def test_sponza_node_counts_bit_exact(sponza_pt):
     counts, _ = scene.bvh_visualizer_node_counts(cam, w, h)
     expected, _ = O.oracle_node_counts(sponza_pt.bvh_nodes, tris, rf.camera_to_array(cam), w, h, rf.FLT_MAX)
     assert np.array_equal(counts, expected)
+    scene.set_kernel(2)
+    counts2, _ = scene.bvh_visualizer_node_counts(cam, w, h)
+    assert np.array_equal(counts2, expected)
     assert 85 < counts.mean() < 95 and counts.max() < 1000  # SURVEY.md §6 probe: mean 89.7, max 369
 
 
-def test_ray_intersect_bvh_batch_bit_exact(duck_pt, golden):
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_ray_intersect_bvh_batch_bit_exact(duck_pt, golden, kernel):
     """The reference's tests/bvh.cpp grid + random/axis-parallel rays: hit, p, t, nodesVisited bit-exact."""
     g = golden["ref_duck_bvh_test"]
     tris = O.triangles9(duck_pt)
     scene = rf.TraversalScene(duck_pt.bvh_nodes, tris)
+    scene.set_kernel(kernel)
     hit, p_t, visited = scene.ray_intersect_bvh(g["rays"].reshape(-1, 6), 1000.0)
     assert np.array_equal(hit, g["hit"])
     assert np.array_equal(p_t.view(np.uint32), g["p_t"].view(np.uint32))

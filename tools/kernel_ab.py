@@ -32,7 +32,9 @@ def main():
         params = rf.RenderParameters((w, h), rf.fly_camera(w, h), rf.SamplingParams(1, 8), rf.Sky(), 0.25)
         ren = rf.ReferencePathTracer(params, (w, h), scene)
         for cfg in args.configs.split(","):
-            kernel, variant, sub_frames, blocks, tri_min, refill_min = (int(x) for x in cfg.split(":"))
+            fields = [int(x) for x in cfg.split(":")]
+            kernel, variant, sub_frames, blocks, tri_min, refill_min = fields[:6]
+            evict = fields[6] if len(fields) > 6 else -1
             ren.set_option("trace_kernel", kernel)
             if kernel == 2:
                 ren.set_option("pair_variant", variant)
@@ -43,6 +45,7 @@ def main():
                 name, value = item.split("=")
                 ren.set_option(name, int(value))
             ren.set_tuning(tri_min, refill_min, blocks)
+            ren.set_tail_policy(evict)
             for k in range(args.frames + 2):
                 if k == 2:
                     ren.reset_stats()

@@ -91,6 +91,21 @@ int main(int argc, char** argv)
 
     std::uint64_t visits = 0, loadsRef = 0, expands = 0, freePops = 0, hitPops = 0, pushes = 0, pushesDefiniteMiss = 0, pushesAlways = 0, mismatches = 0;
     std::uint64_t depthHist[40] = {}, depthHistSkip[40] = {}, triTests = 0, leafVisits = 0;
+    // breadth-first rank of every record (what a top-of-tree treelet in shared memory would hold first)
+    std::vector<std::uint32_t> bfsRank(ps.records.size(), 0xFFFFFFFFu);
+    {
+        std::vector<std::uint32_t> queue;
+        if (!pairLinkIsLeaf(ps.rootLink)) queue.push_back(ps.rootLink);
+        for (std::size_t head = 0; head < queue.size(); ++head)
+        {
+            const std::uint32_t r = queue[head];
+            bfsRank[r] = static_cast<std::uint32_t>(head);
+            if (!pairLinkIsLeaf(ps.records[r].link0)) queue.push_back(ps.records[r].link0);
+            if (!pairLinkIsLeaf(ps.records[r].link1)) queue.push_back(ps.records[r].link1);
+        }
+    }
+    const std::uint32_t treeletSizes[8] = {64, 128, 256, 512, 1024, 2048, 4096, 8192};
+    std::uint64_t       treeletHits[8] = {};
     for (std::size_t r = 0; r < kinds.size(); ++r)
     {
         const float* o = &rays[6 * r];
@@ -162,6 +177,7 @@ int main(int argc, char** argv)
                 {
                     // EXPAND: one record, two slab tests
                     ++expands;
+                    for (int k = 0; k < 8; ++k) treeletHits[k] += bfsRank[link] < treeletSizes[k];
                     const PairRecord& rec = ps.records[link];
                     const Slab        s0 = slab(rec.box0, rec.box0 + 3, o, inv, neg), s1 = slab(rec.box1, rec.box1 + 3, o, inv, neg);
                     const bool        nearIsSecond = neg[rec.meta];
@@ -217,6 +233,7 @@ int main(int argc, char** argv)
     std::printf("per ray: visits %.2f (= node loads of the per-node layout)  records loaded %.2f  triangle tests %.2f  leaf visits %.2f\n", visits / n, expands / n, triTests / n, leafVisits / n);
     std::printf("pops: %.2f hit, %.2f free misses per ray;  pushes %.2f per ray: %.1f%% definite misses, %.1f%% always-hit (tmin <= 0)\n", hitPops / n, freePops / n, pushes / n,
                 100.0 * pushesDefiniteMiss / pushes, 100.0 * pushesAlways / pushes);
+    for (int k = 0; k < 8; ++k) std::printf("records loaded from the first %5u records in breadth-first order: %.1f%%\n", treeletSizes[k], 100.0 * treeletHits[k] / expands);
     std::printf("max stack depth per ray (all far children pushed / definite misses not pushed):\n");
     std::uint64_t cum = 0, cumSkip = 0;
     for (int k = 0; k < 40; ++k)
