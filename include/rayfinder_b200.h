@@ -298,6 +298,9 @@ rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
  *                  child-pair records, one per interior node entered (csrc/traversal_pairs.cuh)
  *   "pair_variant" scheduling variant of the child-pair kernel: bits 0-1 = rounds per warp vote - 1, bit 2 = closest-hit rays
  *                  do not push far children that miss whatever tmax is (1, 3, 5 or 7)
+ *   "tail_window_mode" how the warp-per-ray tail kernel fetches its 32-node windows: 0 = one LDG.256 per lane; 1 = one
+ *                  1 KB bulk asynchronous copy (cp.async.bulk + mbarrier) into shared memory, with the window of the newest
+ *                  out-of-window stack entry copied ahead of time while the current window is walked (csrc/straggler.cuh)
  *   "stage_debug"  1: print the per-launch spans of every stage-timed frame to stderr
  *   "mega_debug"   1: print the persistent kernel's control block after every frame (synchronises) */
 rf_status rf_renderer_set_option(rf_renderer* r, const char* name, int64_t value);

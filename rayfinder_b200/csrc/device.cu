@@ -520,6 +520,7 @@ struct rf_renderer
     std::uint32_t traceStackEntries() const { return std::max(forcedStackEntries, stackEntries); }
     std::uint32_t evictDelay = 4; // rounds a warp keeps its last rays before handing them over (measured: 4 lets the many short ones end in place)
     bool          stageDebug = false, megaDebug = false;
+    int           stragglerWindowMode = STRAGGLER_DIRECT; // how the tail kernel fetches its node windows (straggler.cuh)
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
@@ -796,8 +797,13 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         const auto           finishStragglers = [&](std::uint32_t k, const PathQueue& closestQueue, const PathQueue& shadowQueue) {
             if (evictMax == 0u) return;
             // persistent warps, one ray at a time each; blocks beyond the number of records exit at once
-            k_trace_stragglers<<<r->numSms * STRAGGLER_WARPS_PER_SM / STRAGGLER_WARPS_PER_BLOCK, STRAGGLER_BLOCK_THREADS, 0, ss>>>(
-                sfp, scene, closestQueue, sf.hits.ptr, shadowQueue, r->radiance.ptr, &stragglerCursors[k], stragglersOf(k), r->stats.ptr);
+            const int tailGrid = r->numSms * STRAGGLER_WARPS_PER_SM / STRAGGLER_WARPS_PER_BLOCK;
+            if (r->stragglerWindowMode == STRAGGLER_BULK)
+                k_trace_stragglers<STRAGGLER_BULK><<<tailGrid, STRAGGLER_BLOCK_THREADS, 0, ss>>>(
+                    sfp, scene, closestQueue, sf.hits.ptr, shadowQueue, r->radiance.ptr, &stragglerCursors[k], stragglersOf(k), r->stats.ptr);
+            else
+                k_trace_stragglers<STRAGGLER_DIRECT><<<tailGrid, STRAGGLER_BLOCK_THREADS, 0, ss>>>(
+                    sfp, scene, closestQueue, sf.hits.ptr, shadowQueue, r->radiance.ptr, &stragglerCursors[k], stragglersOf(k), r->stats.ptr);
         };
 
         k_raygen<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
@@ -1220,6 +1226,7 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
     else if (key == "trace_stack") r->forcedStackEntries = static_cast<std::uint32_t>(std::min<std::int64_t>(value, RF_STACK_SIZE));
     else if (key == "trace_kernel" && value <= 2) r->traceKernel = static_cast<int>(value);
     else if (key == "pair_variant" && value <= 7) r->pairVariant = static_cast<int>(value);
+    else if (key == "tail_window_mode" && value <= 1) r->stragglerWindowMode = static_cast<int>(value);
     else if (key == "stage_debug") r->stageDebug = value != 0;
     else if (key == "mega_debug") r->megaDebug = value != 0;
     else return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: unknown option '%s'", name);

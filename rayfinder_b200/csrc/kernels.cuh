@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_tr
 // loads 32 consecutive nodes per memory round trip, tests them lane-parallel and walks the ray through the
 // results, ~3x faster per ray than a lone lane of the persistent loop.  Warps take records one at a time.
 constexpr int STRAGGLER_BLOCK_THREADS = STRAGGLER_WARPS_PER_BLOCK * 32;
+template<int WINDOW_MODE>
 __global__ void __launch_bounds__(STRAGGLER_BLOCK_THREADS) k_trace_stragglers(
     const FrameParams     fp,
     const SceneDevice     scene,
@@ -533,6 +534,18 @@ __global__ void __launch_bounds__(STRAGGLER_BLOCK_THREADS) k_trace_stragglers(
     if (threadIdx.x < 6) blockStats[threadIdx.x] = 0u;
     __syncthreads();
     TraceIO io{{fetchCursor, numRecords}, stragglers, fp, scene, closestQueue, 0u, hits, shadowQueue, radiance, v3(fp.sky.sun_direction), blockStats};
+    StragglerWarpShared& mySh = warpShared[threadIdx.x >> 5];
+    std::uint32_t        barrierParity = 0;
+    if (WINDOW_MODE == STRAGGLER_BULK)
+    {
+        if (laneId() == 0u)
+        {
+            mbarrierInit(sharedAddress(&mySh.barrier[0]), 1u);
+            mbarrierInit(sharedAddress(&mySh.barrier[1]), 1u);
+            fenceProxyAsync(); // the barriers must be visible to the async proxy before the first copy names them
+        }
+        __syncwarp();
+    }
 #ifdef RF_TRACE_TIMELINE
     const unsigned long long tlStart = globalTimerNs();
     std::uint32_t            tlRays = 0;
@@ -543,7 +556,7 @@ __global__ void __launch_bounds__(STRAGGLER_BLOCK_THREADS) k_trace_stragglers(
         if (laneId() == 0u) idx = atomicAdd(fetchCursor, 1u);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= numRecords) break;
-        traceStragglerWarp(scene.nodes, scene.tris, stragglers.records + idx, warpShared[threadIdx.x >> 5], io);
+        traceStragglerWarp<WINDOW_MODE>(scene.nodes, scene.tris, stragglers.records + idx, mySh, barrierParity, io);
 #ifdef RF_TRACE_TIMELINE
         ++tlRays;
 #endif

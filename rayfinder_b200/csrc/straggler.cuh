@@ -19,6 +19,7 @@
 // is unchanged, so hits, node counts and triangle counts stay bit-identical (tests: scheduling independence).
 #pragma once
 
+#include "bulk_copy.cuh"
 #include "traversal.cuh"
 
 namespace rfb200
@@ -27,11 +28,26 @@ constexpr int STRAGGLER_WARPS_PER_BLOCK = 4;
 constexpr int STRAGGLER_WARPS_PER_SM = 32; // measured: 16 is slower, 64 no faster
 constexpr int STRAGGLER_WINDOW = 32; // nodes per window = one per lane
 
-struct StragglerWarpShared
+struct __align__(16) StragglerWarpShared
 {
     uint4         node[STRAGGLER_WINDOW]; // (tmin bits, a, b, flags)
     uint4         tri[STRAGGLER_WINDOW];  // first triangle of a leaf: (valid, u bits, v bits, t bits)
     std::uint32_t stack[RF_STACK_SIZE];
+    // bulk-copy mode: two staging buffers of one raw window each, filled by cp.async.bulk — [0] on demand, [1] ahead of time
+    PackedNode         raw[2][STRAGGLER_WINDOW];
+    unsigned long long barrier[2]; // their mbarriers
+};
+
+// How a window reaches the warp (compile time; results never depend on it):
+//   STRAGGLER_DIRECT  every lane loads its node of the window with one LDG.256 (round 1)
+//   STRAGGLER_BULK    the window is staged in shared memory by ONE bulk asynchronous copy of 1 KB (cp.async.bulk through the
+//                     TMA unit, completion on an mbarrier), and while the warp walks a window the copy of the window it will
+//                     most probably need next — the one of the newest stack entry that lies outside the current window — is
+//                     already in flight into a second buffer: the L2 round trip of a window switch overlaps the walk
+enum StragglerWindowMode : int
+{
+    STRAGGLER_DIRECT = 0,
+    STRAGGLER_BULK = 1
 };
 
 constexpr std::uint32_t WIN_OK = 1u;  // tmin <= tmx && tmx > 0 (the tmax-independent part of the slab test)
@@ -39,12 +55,13 @@ constexpr std::uint32_t WIN_NAN = 2u; // a slab product was NaN: re-test with th
 
 // Traces the ray of `rec` to its end on the calling warp (all 32 lanes, converged) and returns its result in
 // (hit, rayNodes, rayTris) on every lane.
-template<class IO>
+template<int WINDOW_MODE, class IO>
 __device__ __forceinline__ void traceStragglerWarp(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
     const StragglerRecord* rec,
     StragglerWarpShared&   sh,
+    std::uint32_t&         barrierParity, // bulk-copy mode: bit b = phase parity the next wait on sh.barrier[b] expects (kept by the caller across rays)
     IO&                    io)
 {
     const std::uint32_t lane = laneId();
@@ -75,6 +92,29 @@ __device__ __forceinline__ void traceStragglerWarp(
     PackedNode    mine{};             // this lane's node of the window (kept for the literal re-test)
     bool          done = state == 3;
 
+    // ---- bulk-copy mode: staging buffers and their barriers (one warp owns them; phases persist across rays) -----------
+    constexpr std::uint32_t WINDOW_BYTES = STRAGGLER_WINDOW * sizeof(PackedNode);
+    const std::uint32_t     bar0 = sharedAddress(&sh.barrier[0]), bar1 = sharedAddress(&sh.barrier[1]);
+    std::uint32_t           aheadBase = 0x80000000u; // window in flight into (or sitting in) raw[1]; none: 0x80000000
+    const auto issueCopy = [&](const int buffer, const std::uint32_t first) {
+        // every lane has finished reading the buffer (the caller synchronised the warp) before the copy overwrites it.  No
+        // proxy fence here: it is needed after generic-proxy WRITES that the async proxy must see, not after reads — and on
+        // sm_100a it costs an L1 invalidation (SYNCS.CCTL.IVALL), which made this kernel 7 % slower when it sat here.
+        if (lane == 0u)
+        {
+            const std::uint32_t bar = buffer ? bar1 : bar0;
+            mbarrierArriveExpectTx(bar, WINDOW_BYTES);
+            bulkCopyGlobalToShared(sharedAddress(&sh.raw[buffer][0]), nodes + first, WINDOW_BYTES, bar);
+        }
+    };
+    // Copy the window at `first` ahead of time if the second buffer is free.
+    const auto copyAhead = [&](const std::uint32_t first) {
+        if (WINDOW_MODE != STRAGGLER_BULK || aheadBase != 0x80000000u) return;
+        __syncwarp();
+        aheadBase = first;
+        issueCopy(1, first);
+    };
+
     // Window [first, first + 32): lane L takes node first + L.  (The node array is padded with 64 zeroed records,
     // which read as never-visited interior nodes, so the window may run past the last node.)
     const auto loadWindow = [&](const std::uint32_t first) {
@@ -83,7 +123,22 @@ __device__ __forceinline__ void traceStragglerWarp(
         ++tlWindows;
 #endif
         base = first;
-        mine = loadNode(nodes + first + lane);
+        if (WINDOW_MODE == STRAGGLER_BULK)
+        {
+            const int buffer = aheadBase == first ? 1 : 0;
+            if (buffer == 0) issueCopy(0, first);
+            const std::uint32_t bar = buffer ? bar1 : bar0;
+            while (!mbarrierTryWait(bar, (barrierParity >> buffer) & 1u)) {}
+            barrierParity ^= 1u << buffer;
+            if (buffer == 1) aheadBase = 0x80000000u;
+            const uint4* src = reinterpret_cast<const uint4*>(&sh.raw[buffer][lane]);
+            const uint4  lo = src[0], hi = src[1];
+            mine = PackedNode{__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w), __uint_as_float(hi.x), __uint_as_float(hi.y), hi.z, hi.w};
+        }
+        else
+        {
+            mine = loadNode(nodes + first + lane);
+        }
         const float x0 = (mine.minX - o.x) * ix, x1 = (mine.maxX - o.x) * ix;
         const float y0 = (mine.minY - o.y) * iy, y1 = (mine.maxY - o.y) * iy;
         const float z0 = (mine.minZ - o.z) * iz, z1 = (mine.maxZ - o.z) * iz;
@@ -100,6 +155,12 @@ __device__ __forceinline__ void traceStragglerWarp(
             sh.tri[lane] = make_uint4(valid ? 1u : 0u, __float_as_uint(u), __float_as_uint(v), __float_as_uint(t));
         }
         __syncwarp();
+        // ... and while this window is walked, fetch the one the newest stack entry leads to
+        if (WINDOW_MODE == STRAGGLER_BULK && sp != 0u)
+        {
+            const std::uint32_t top = sh.stack[sp - 1u];
+            if (top - base >= static_cast<std::uint32_t>(STRAGGLER_WINDOW)) copyAhead(top);
+        }
     };
 
     // Triangles [first, end) of a leaf, in order, against the current tmax: one triangle per lane, then the
@@ -170,8 +231,11 @@ __device__ __forceinline__ void traceStragglerWarp(
         if (boxHit && kind != 3u)
         {
             const bool neg = (negMask >> kind) & 1u;
-            sh.stack[sp++] = neg ? cur + 1u : e.y; // every lane stores the same word
+            const std::uint32_t pushed = neg ? cur + 1u : e.y;
+            sh.stack[sp++] = pushed; // every lane stores the same word
             cur = neg ? e.y : cur + 1u;
+            // the newest entry outside the window is where the walk goes when it leaves the window by a pop
+            if (WINDOW_MODE == STRAGGLER_BULK && pushed - base >= static_cast<std::uint32_t>(STRAGGLER_WINDOW)) copyAhead(pushed);
             continue;
         }
         if (boxHit)
@@ -195,6 +259,12 @@ __device__ __forceinline__ void traceStragglerWarp(
         needPop = true;
     }
 
+    if (WINDOW_MODE == STRAGGLER_BULK && aheadBase != 0x80000000u)
+    {
+        // a copy the ray did not get to use is still in flight: let it land before the buffer serves the next ray
+        while (!mbarrierTryWait(bar1, (barrierParity >> 1) & 1u)) {}
+        barrierParity ^= 2u;
+    }
     V3    o2 = o, d2 = d;
     float tmax2 = tmax;
     bool  anyHit2 = anyHit;

@@ -352,8 +352,8 @@ def test_results_do_not_depend_on_scheduling(duck_pt, kernel, sub_frames, persis
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("evict_max,sub_frames", [(1, 1), (8, 1), (32, 2), (-1, -1)])
-def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames):
+@pytest.mark.parametrize("evict_max,sub_frames,window_mode", [(1, 1, 0), (8, 1, 0), (32, 2, 0), (-1, -1, 0), (8, 1, 1), (32, 2, 1), (-1, -1, 1)])
+def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames, window_mode):
     """The warp-per-ray tail kernel (csrc/straggler.cuh: 32-node windows, lane-parallel slab and first-triangle tests,
     one triangle per lane in multi-triangle leaves) resumes rays in mid-traversal.  On Sponza's long grazing rays —
     including the 1/256 of the shadow rays that are axis-parallel and take the NaN re-test — every counter and
@@ -370,6 +370,7 @@ def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames):
     assert ref_stats["evict_max"] == 0 and ref_stats["sub_frames"] == 1
     ren2, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
     ren2.set_option("trace_kernel", 1)
+    ren2.set_option("tail_window_mode", window_mode)  # 1: windows staged by cp.async.bulk + mbarrier, next window copied ahead
     ren2.set_pipeline(sub_frames, 0, 3, 256)
     ren2.set_tail_policy(evict_max)
     ren2.render(), ren2.render()
