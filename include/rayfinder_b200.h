@@ -475,6 +475,19 @@ rf_status rf_pt_add_texture(rf_pt_file* f, const uint32_t* pixels, uint32_t widt
  * room for rf_pt_num_textures(f) entries. */
 rf_status rf_pt_scene(const rf_pt_file* f, rf_scene* out, rf_texture* textures);
 
+/* ---- scene baking: nlrs::PtFormat(gltfPath) (pt-format/pt_format.cpp:20-151), the step before the path ---------- */
+
+/* Texture::fromMemory (common/texture.cpp:12-52): decode a PNG or baseline JPEG as stbi_load_from_memory(..., 4) does and
+ * pack b | g << 8 | r << 16 | 255 << 24.  out_bgra == NULL queries the size; otherwise it needs width * height entries. */
+rf_status rf_texture_from_memory(const void* data, uint64_t size, uint32_t* out_bgra, uint64_t capacity_pixels, uint32_t* width, uint32_t* height);
+
+/* PtFormat(std::filesystem::path gltfPath) (pt-format/pt_format.cpp:20-151): GltfModel (common/gltf_model.cpp:266-465) ->
+ * FlattenedModel (common/flattened_model.cpp:8-46) -> buildBvh + reorderAttributes -> the arrays serialize() writes.  Reads
+ * .glb and .gltf (external or base64 buffers and images); host only.  Errors carry the reference's messages ("The gltf file
+ * {} does not exist.", "Failed to parse gltf file {}.", "Failed to load gltf buffers for {}.", "The image {} does not
+ * exist.").  pt-format-tool (pt-format-tool/main.cpp:14-35) = rf_bake_gltf + rf_pt_save. */
+rf_status rf_bake_gltf(const char* gltf_path, rf_pt_file** out);
+
 /* Introspection used by the tests / bench: 1 when built with CUDA kernels for sm_100a. */
 int32_t     rf_has_cuda_kernels(void);
 const char* rf_build_info(void);

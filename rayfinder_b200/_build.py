@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False, timeline: bool = False) ->
         if src.suffix == ".cu":
             (OBJ / (src.name + ".ptxas.txt")).write_text(res.stderr)
         objs.append(str(obj))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs, "-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -83,7 +83,7 @@ def _build_timeline(verbose: bool, defines=(), suffix: str = "") -> Path:
     if res.returncode != 0:
         raise RuntimeError("timeline build failed")
     objs = [str(obj)] + [str(OBJ / (src.name + ".o")) for src in sorted(CSRC.glob("*.cpp")) + sorted(CSRC.glob("*.cu")) if src.name != "device.cu"]
-    res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], capture_output=True, text=True)
+    res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs, "-lz"], capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("link failed")

@@ -146,6 +146,8 @@ SIGNATURES = {
     "rf_pt_texture": (C.c_int32, [_P, C.c_uint64, C.POINTER(Texture)]),
     "rf_pt_add_texture": (C.c_int32, [_P, _P, C.c_uint32, C.c_uint32]),
     "rf_pt_scene": (C.c_int32, [_P, C.POINTER(Scene), C.POINTER(Texture)]),
+    "rf_texture_from_memory": (C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rf_bake_gltf": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
     "rf_has_cuda_kernels": (C.c_int32, []),
     "rf_build_info": (C.c_char_p, []),
 }

@@ -9,6 +9,7 @@
 //   [u64 numTextures] { [u32 width][u32 height][u64 numPixels][numPixels * u32 BGRA] }  (:220-225)
 //
 // Little-endian, packed, struct padding bytes included.  Host-only code.
+#include "pt_file.h"
 #include "rf_internal.h"
 
 #include <cstdio>
@@ -24,24 +25,9 @@ using namespace rfb200;
 
 namespace
 {
-constexpr char          MAGIC[] = "PTFORMAT3";
-constexpr std::size_t   MAGIC_LEN = 9;
-constexpr std::uint64_t ELEM_SIZE[RF_PT_NUM_ARRAYS] = {48, 36, 48, 80, 16, 16, 8, 4, 16, 16, 16, 16, 4};
-
-struct TextureData
-{
-    std::uint32_t              width = 0, height = 0;
-    std::vector<std::uint32_t> pixels;
-};
+constexpr char        MAGIC[] = "PTFORMAT3";
+constexpr std::size_t MAGIC_LEN = 9;
 } // namespace
-
-struct rf_pt_file
-{
-    std::vector<std::uint8_t> arrays[RF_PT_NUM_ARRAYS];
-    std::vector<TextureData>  textures;
-
-    std::uint64_t count(int which) const { return arrays[which].size() / ELEM_SIZE[which]; }
-};
 
 namespace
 {
@@ -93,8 +79,8 @@ rf_status parse(const std::uint8_t* data, std::uint64_t size, rf_pt_file& f)
     const auto readArray = [&](int which) {
         const std::uint64_t n = r.u64();
         if (!r.ok) return;
-        const std::uint64_t bytes = n * ELEM_SIZE[which];
-        if (n != 0 && (bytes / ELEM_SIZE[which] != n || static_cast<std::uint64_t>(r.end - r.cur) < bytes))
+        const std::uint64_t bytes = n * RF_PT_ELEM_SIZE[which];
+        if (n != 0 && (bytes / RF_PT_ELEM_SIZE[which] != n || static_cast<std::uint64_t>(r.end - r.cur) < bytes))
         {
             r.ok = false;
             return;
@@ -131,7 +117,7 @@ rf_status parse(const std::uint8_t* data, std::uint64_t size, rf_pt_file& f)
         else
         {
             f.textures.resize(numTextures);
-            for (TextureData& t : f.textures)
+            for (PtTextureData& t : f.textures)
             {
                 r.read(&t.width, 4);
                 r.read(&t.height, 4);
@@ -166,7 +152,7 @@ std::uint64_t serializedSize(const rf_pt_file& f)
     std::uint64_t n = MAGIC_LEN;
     for (int a = 0; a < RF_PT_NUM_ARRAYS; ++a) n += 8 + f.arrays[a].size();
     n += 8;
-    for (const TextureData& t : f.textures) n += 16 + 4 * t.pixels.size();
+    for (const PtTextureData& t : f.textures) n += 16 + 4 * t.pixels.size();
     return n;
 }
 
@@ -185,7 +171,7 @@ void serializeTo(const rf_pt_file& f, std::uint8_t* dst)
     }
     const std::uint64_t numTextures = f.textures.size();
     put(&numTextures, 8);
-    for (const TextureData& t : f.textures)
+    for (const PtTextureData& t : f.textures)
     {
         put(&t.width, 4);
         put(&t.height, 4);
@@ -301,17 +287,17 @@ extern "C" rf_status rf_pt_array(const rf_pt_file* f, int32_t which, const void*
     if (!f || which < 0 || which >= RF_PT_NUM_ARRAYS) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_array: bad argument");
     if (data) *data = f->arrays[which].data();
     if (count) *count = f->count(which);
-    if (elem_size) *elem_size = ELEM_SIZE[which];
+    if (elem_size) *elem_size = RF_PT_ELEM_SIZE[which];
     return RF_OK;
 }
 
 extern "C" rf_status rf_pt_set_array(rf_pt_file* f, int32_t which, const void* data, std::uint64_t count)
 {
     if (!f || which < 0 || which >= RF_PT_NUM_ARRAYS || (!data && count)) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_set_array: bad argument");
-    if (count > (~0ull >> 1) / ELEM_SIZE[which]) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_set_array: count out of range");
+    if (count > (~0ull >> 1) / RF_PT_ELEM_SIZE[which]) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_set_array: count out of range");
     return guarded("rf_pt_set_array", [&]() -> rf_status {
         const auto* p = static_cast<const std::uint8_t*>(data);
-        f->arrays[which].assign(p, p + count * ELEM_SIZE[which]);
+        f->arrays[which].assign(p, p + count * RF_PT_ELEM_SIZE[which]);
         return RF_OK;
     });
 }
@@ -321,7 +307,7 @@ extern "C" std::uint64_t rf_pt_num_textures(const rf_pt_file* f) { return f ? f-
 extern "C" rf_status rf_pt_texture(const rf_pt_file* f, std::uint64_t idx, rf_texture* out)
 {
     if (!f || !out || idx >= f->textures.size()) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_texture: bad argument");
-    const TextureData& t = f->textures[idx];
+    const PtTextureData& t = f->textures[idx];
     *out = rf_texture{t.pixels.data(), t.width, t.height};
     return RF_OK;
 }
@@ -330,7 +316,7 @@ extern "C" rf_status rf_pt_add_texture(rf_pt_file* f, const std::uint32_t* pixel
 {
     if (!f || !pixels) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_pt_add_texture: null argument");
     return guarded("rf_pt_add_texture", [&]() -> rf_status {
-        TextureData t;
+        PtTextureData t;
         t.width = width, t.height = height;
         t.pixels.assign(pixels, pixels + static_cast<std::uint64_t>(width) * height);
         f->textures.push_back(std::move(t));
