@@ -35,33 +35,42 @@ def main():
     ren = rf.ReferencePathTracer(params, (w, h), rf.SceneArrays.from_pt(pt), device=local)
     ren.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     ren.set_tile_partition(rank, world)
+    spp = 3  # progressive: the exchange runs after every frame and must hand over the k-sample sum each time
+    params.sampling_params = rf.SamplingParams(spp, bounces)
     results = {}
     for mode in ("nccl", "p2p"):
         exchange = rfd.HdrExchange(ren, w, h, mode=mode)
-        for frame in range(2):  # two frames: the second restarts the accumulation while the buffers are in use
-            params.exposure = 0.25 + 0.1 * frame
-            ren.set_render_parameters(params)
-            ren.reset_stats()
+        params.exposure = 0.25 if mode == "nccl" else 0.35  # restarts the accumulation while the buffers are in use
+        ren.set_render_parameters(params)
+        ren.set_frame_count(0)
+        ren.reset_stats()
+        frames = []
+        for frame in range(spp):
             ren.render()
             hdr = exchange()
+            if rank == 0:
+                frames.append(hdr.cpu().numpy().copy())
         torch.cuda.synchronize(dev)
         paths = torch.tensor([ren.stats()["paths"]], dtype=torch.int64, device=dev)
         dist.all_reduce(paths)
         if rank == 0:
-            results[exchange.mode] = (hdr.cpu().numpy().copy(), int(paths[0]))
+            results[exchange.mode] = (frames, int(paths[0]))
         dist.barrier()
         exchange.close()
     if rank == 0:
         ren.set_tile_partition(0, 1)
         params.exposure = 0.9
         ren.set_render_parameters(params)
-        ren.render()
-        single, _ = ren.read_hdr()
-        for mode, (image, paths) in results.items():
-            same = np.array_equal(image.view(np.uint32), single.view(np.uint32))
-            print(f"world={world} {w}x{h} bounces={bounces} exchange={mode}: paths={paths} (expected {w * h}), "
-                  f"image on rank 0 bit-identical to single GPU: {same}", flush=True)
-            assert same and paths == w * h
+        ren.set_frame_count(0)
+        singles = []
+        for frame in range(spp):
+            ren.render()
+            singles.append(ren.read_hdr()[0])
+        for mode, (frames, paths) in results.items():
+            same = all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(frames, singles))
+            print(f"world={world} {w}x{h} bounces={bounces} spp={spp} exchange={mode}: paths={paths} (expected {spp * w * h}), "
+                  f"image on rank 0 after every frame bit-identical to single GPU: {same}", flush=True)
+            assert same and paths == spp * w * h
         assert "p2p" in results or world == 1, "peer-memory exchange was not available"
     dist.barrier()
     dist.destroy_process_group()
