@@ -435,6 +435,14 @@ rf_status rf_build_bvh_device(
     uint64_t*           out_triangle_indices,
     float*              out_device_ms);
 
+/* 0 (default): the build is one persistent launch with grid-wide barriers between its phases; 1: one launch per phase and
+ * level (round 1's path, kept for A/B timing).  Same bytes either way.  Process-wide. */
+void rf_build_bvh_device_set_mode(int32_t level_kernels);
+/* Diagnostics of the last single-launch build: milliseconds its first block spent in each phase, summed over the levels
+ * (12 floats: boxes, decide, buckets, sweep, scan, offsets, pair, permute, level bookkeeping, numbering, emit, unused);
+ * returns the number of levels. */
+uint32_t rf_build_bvh_device_last_phases(float* out_phase_ms);
+
 /* ---- .pt container: nlrs::PtFormat + serialize/deserialize (pt-format/pt_format.hpp:18-43) ----- */
 
 typedef struct rf_pt_file rf_pt_file;

@@ -27,6 +27,9 @@ NVCC_FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-Xptxas", "-v",
 ]
+# bvh_build.cu: its single-launch builder passes data between blocks through global memory inside one kernel, so plain global
+# loads must not be served from a (non-coherent) L1 line: cache them in L2 only.
+EXTRA_NVCC_FLAGS = {"bvh_build.cu": ["-Xptxas", "-dlcm=cg"]}
 CXX_FLAGS = ["-std=c++20", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra",
              f'-DRF_DATA_DIR="{DATA}"']
 
@@ -51,7 +54,7 @@ def build(force: bool = False, verbose: bool = False, timeline: bool = False) ->
     for src in sources:
         obj = OBJ / (src.name + ".o")
         if src.suffix == ".cu":
-            cmd = [NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [NVCC, *NVCC_FLAGS, *EXTRA_NVCC_FLAGS.get(src.name, []), "-c", str(src), "-o", str(obj)]
         else:
             cmd = [CXX, *CXX_FLAGS, "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 namespace rfb200
@@ -143,10 +144,10 @@ __global__ void k_bvh_root(BuildNode* nodes, NodeAccum* accum, const std::uint32
 }
 
 // ---- boxes: fold every primitive of an open node into the node's accumulators ------------------------------------
-__global__ void k_bvh_boxes(const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
-                            const std::uint32_t* __restrict__ owner, NodeAccum* accum)
+// (called by whole warps: lane L handles position i = warpBase + L)
+__device__ __forceinline__ void boxesAt(const std::uint32_t i, const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* order,
+                                        const std::uint32_t* owner, NodeAccum* accum)
 {
-    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const std::uint32_t node = i < n ? owner[i] : NONE;
     const bool          active = node != NONE;
     const unsigned      activeMask = __ballot_sync(0xFFFFFFFFu, active);
@@ -177,14 +178,16 @@ __global__ void k_bvh_boxes(const std::uint32_t n, const Prim* __restrict__ prim
         atomicMax(&a.centHi[k], ch);
     }
 }
+__global__ void k_bvh_boxes(const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
+                            const std::uint32_t* __restrict__ owner, NodeAccum* accum)
+{
+    boxesAt(blockIdx.x * blockDim.x + threadIdx.x, n, prims, order, owner, accum);
+}
 
 // ---- decide: leaf / two-primitive median split / SAH (bvh.cpp:96-140) --------------------------------------------
-__global__ void k_bvh_decide(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes, NodeAccum* accum,
-                             BucketAccum* buckets, const Prim* __restrict__ prims, std::uint32_t* order, std::uint32_t* owner,
-                             std::uint32_t* counters /* [0] node slots, [1] bucket slots of this level */)
+__device__ __forceinline__ void decideAt(const std::uint32_t s, BuildNode* nodes, NodeAccum* accum, BucketAccum* buckets, const Prim* __restrict__ prims,
+                                         std::uint32_t* order, std::uint32_t* owner, std::uint32_t* counters /* [0] node slots, [1] bucket slots of this level */)
 {
-    const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= levelEnd) return;
     BuildNode        nd = nodes[s];
     const NodeAccum& a = accum[s];
     // the winners of the key reductions are positions; the box takes their actual bits (signed zeros included)
@@ -245,13 +248,17 @@ __global__ void k_bvh_decide(const std::uint32_t levelBegin, const std::uint32_t
     }
     nodes[s] = nd;
 }
+__global__ void k_bvh_decide(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes, NodeAccum* accum,
+                             BucketAccum* buckets, const Prim* __restrict__ prims, std::uint32_t* order, std::uint32_t* owner, std::uint32_t* counters)
+{
+    const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < levelEnd) decideAt(s, nodes, accum, buckets, prims, order, owner, counters);
+}
 
 // ---- buckets: count and bound the primitives of every SAH node per bucket (bvh.cpp:146-156) ----------------------
-__global__ void k_bvh_buckets(const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
-                              const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes, BucketAccum* buckets)
+__device__ __forceinline__ void bucketsAt(const std::uint32_t i, const Prim* __restrict__ prims, const std::uint32_t* order,
+                                          const std::uint32_t* owner, const BuildNode* nodes, BucketAccum* buckets)
 {
-    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const std::uint32_t s = owner[i];
     if (s == NONE) return;
     const BuildNode& nd = nodes[s];
@@ -266,13 +273,17 @@ __global__ void k_bvh_buckets(const std::uint32_t n, const Prim* __restrict__ pr
         atomicMax(&acc.hi[b][k], orderedBits(comp(p.hi, k)));
     }
 }
+__global__ void k_bvh_buckets(const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
+                              const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes, BucketAccum* buckets)
+{
+    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bucketsAt(i, prims, order, owner, nodes, buckets);
+}
 
 // ---- sweep: the SAH decision of every SAH node (bvh.cpp:157-214), children for the ones that split ---------------
-__global__ void k_bvh_sweep(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes, NodeAccum* accum,
-                            const BucketAccum* __restrict__ buckets, std::uint32_t* owner, std::uint32_t* counters)
+__device__ __forceinline__ void sweepAt(const std::uint32_t s, BuildNode* nodes, NodeAccum* accum, const BucketAccum* buckets, std::uint32_t* owner,
+                                        std::uint32_t* counters)
 {
-    const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= levelEnd) return;
     BuildNode nd = nodes[s];
     if (nd.kind != KIND_SAH) return;
     const BucketAccum& acc = buckets[nd.bucketSlot];
@@ -312,6 +323,12 @@ __global__ void k_bvh_sweep(const std::uint32_t levelBegin, const std::uint32_t 
     }
     nodes[s] = nd;
 }
+__global__ void k_bvh_sweep(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes, NodeAccum* accum,
+                            const BucketAccum* __restrict__ buckets, std::uint32_t* owner, std::uint32_t* counters)
+{
+    const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < levelEnd) sweepAt(s, nodes, accum, buckets, owner, counters);
+}
 
 // ---- partition, step 1: (fails, satisfies) flags of the predicate `bucket <= splitBucket` (bvh.cpp:216-221) -------
 __device__ __forceinline__ bool goesLeft(const BuildNode& nd, const Prim& p)
@@ -319,29 +336,30 @@ __device__ __forceinline__ bool goesLeft(const BuildNode& nd, const Prim& p)
     return bvhBucketOf(centroidOf(p, nd.axis), nd.cLo, nd.cHi) <= nd.splitBucket;
 }
 
-__global__ void k_bvh_flags(const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
-                            const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes, unsigned long long* flags)
+__device__ __forceinline__ unsigned long long flagAt(const std::uint32_t i, const std::uint32_t n, const Prim* __restrict__ prims,
+                                                     const std::uint32_t* order, const std::uint32_t* owner, const BuildNode* nodes)
 {
-    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
     unsigned long long f = 0ull; // element n: the scan's total
     if (i < n)
     {
         const std::uint32_t s = owner[i];
         if (s != NONE && nodes[s].kind == KIND_SPLIT) f = goesLeft(nodes[s], prims[order[i]]) ? 1ull : (1ull << 32);
     }
-    flags[i] = f;
+    return f;
+}
+__global__ void k_bvh_flags(const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
+                            const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes, unsigned long long* flags)
+{
+    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) flags[i] = flagAt(i, n, prims, order, owner, nodes);
 }
 
 // ---- partition, steps 2 and 3.  scan[i] = (fails before i) << 32 | (satisfies before i).  Left zone [begin, mid),
 // right zone [mid, end): the k-th failing element of the left zone (from the left) and the k-th satisfying element
 // of the right zone (from the right) trade places — libstdc++'s std::__partition for bidirectional iterators. -------
-__global__ void k_bvh_pair(const std::uint32_t n, const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes,
-                           const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan,
-                           std::uint32_t* slotLeft, std::uint32_t* slotRight)
+__device__ __forceinline__ void pairAt(const std::uint32_t i, const std::uint32_t* owner, const BuildNode* nodes, const unsigned long long* flags,
+                                       const unsigned long long* scan, std::uint32_t* slotLeft, std::uint32_t* slotRight)
 {
-    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const std::uint32_t s = owner[i];
     if (s == NONE) return;
     const BuildNode& nd = nodes[s];
@@ -358,14 +376,18 @@ __global__ void k_bvh_pair(const std::uint32_t n, const std::uint32_t* __restric
         slotRight[nd.begin + k] = i;
     }
 }
-
-__global__ void k_bvh_permute(const std::uint32_t n, std::uint32_t* owner, const BuildNode* __restrict__ nodes,
-                              const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan,
-                              const std::uint32_t* __restrict__ slotLeft, const std::uint32_t* __restrict__ slotRight,
-                              const std::uint32_t* __restrict__ orderIn, std::uint32_t* orderOut)
+__global__ void k_bvh_pair(const std::uint32_t n, const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes,
+                           const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan,
+                           std::uint32_t* slotLeft, std::uint32_t* slotRight)
 {
     const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i < n) pairAt(i, owner, nodes, flags, scan, slotLeft, slotRight);
+}
+
+__device__ __forceinline__ void permuteAt(const std::uint32_t i, std::uint32_t* owner, const BuildNode* nodes, const unsigned long long* flags,
+                                          const unsigned long long* scan, const std::uint32_t* slotLeft, const std::uint32_t* slotRight,
+                                          const std::uint32_t* orderIn, std::uint32_t* orderOut)
+{
     const std::uint32_t s = owner[i];
     std::uint32_t       src = i;
     if (s != NONE && nodes[s].kind == KIND_SPLIT)
@@ -380,20 +402,29 @@ __global__ void k_bvh_permute(const std::uint32_t n, std::uint32_t* owner, const
     }
     orderOut[i] = orderIn[src];
 }
+__global__ void k_bvh_permute(const std::uint32_t n, std::uint32_t* owner, const BuildNode* __restrict__ nodes,
+                              const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan,
+                              const std::uint32_t* __restrict__ slotLeft, const std::uint32_t* __restrict__ slotRight,
+                              const std::uint32_t* __restrict__ orderIn, std::uint32_t* orderOut)
+{
+    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) permuteAt(i, owner, nodes, flags, scan, slotLeft, slotRight, orderIn, orderOut);
+}
 
 // ---- numbering: subtree sizes (deepest level first), pre-order indices (root first), node records ------------------
-__global__ void k_bvh_sizes(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes)
+__device__ __forceinline__ void sizeAt(const std::uint32_t s, BuildNode* nodes)
 {
-    const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= levelEnd) return;
     BuildNode& nd = nodes[s];
     nd.size = nd.kind == KIND_LEAF ? 1u : 1u + nodes[nd.child0].size + nodes[nd.child1].size;
 }
-
-__global__ void k_bvh_preorder(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes)
+__global__ void k_bvh_sizes(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes)
 {
     const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= levelEnd) return;
+    if (s < levelEnd) sizeAt(s, nodes);
+}
+
+__device__ __forceinline__ void preorderAt(const std::uint32_t s, BuildNode* nodes)
+{
     const BuildNode& nd = nodes[s];
     if (s == 0u) nodes[0].preorder = 0u;
     if (nd.kind == KIND_LEAF) return;
@@ -401,11 +432,14 @@ __global__ void k_bvh_preorder(const std::uint32_t levelBegin, const std::uint32
     nodes[nd.child0].preorder = me + 1u;                          // bvh.cpp:93-94: the first child follows its parent
     nodes[nd.child1].preorder = me + 1u + nodes[nd.child0].size;  // the second one follows the first subtree
 }
-
-__global__ void k_bvh_emit(const std::uint32_t numNodes, const BuildNode* __restrict__ nodes, rf_bvh_node* out)
+__global__ void k_bvh_preorder(const std::uint32_t levelBegin, const std::uint32_t levelEnd, BuildNode* nodes)
 {
-    const std::uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= numNodes) return;
+    const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < levelEnd) preorderAt(s, nodes);
+}
+
+__device__ __forceinline__ void emitAt(const std::uint32_t s, const BuildNode* nodes, rf_bvh_node* out)
+{
     const BuildNode& nd = nodes[s];
     rf_bvh_node      o{}; // padding words are zero, as in the reference's aggregate initialisation
     o.aabb_min[0] = nd.box.lo.x, o.aabb_min[1] = nd.box.lo.y, o.aabb_min[2] = nd.box.lo.z;
@@ -420,11 +454,321 @@ __global__ void k_bvh_emit(const std::uint32_t numNodes, const BuildNode* __rest
     }
     out[nd.preorder] = o;
 }
+__global__ void k_bvh_emit(const std::uint32_t numNodes, const BuildNode* __restrict__ nodes, rf_bvh_node* out)
+{
+    const std::uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < numNodes) emitAt(s, nodes, out);
+}
 
 __global__ void k_bvh_indices(const std::uint32_t n, const std::uint32_t* __restrict__ order, unsigned long long* triangleIndices)
 {
     const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) triangleIndices[order[i]] = i; // bvh.cpp:64-69: old index -> position in leaf order
+}
+
+// warp min / max of 64-bit keys over the lanes of `mask` (all lanes of `mask` call)
+__device__ __forceinline__ unsigned long long __reduce_min_sync_u64(const unsigned mask, unsigned long long v)
+{
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const unsigned long long other = __shfl_xor_sync(mask, v, d);
+        const bool               valid = (mask >> ((threadIdx.x & 31u) ^ static_cast<unsigned>(d))) & 1u;
+        if (valid && other < v) v = other;
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned long long __reduce_max_sync_u64(const unsigned mask, unsigned long long v)
+{
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const unsigned long long other = __shfl_xor_sync(mask, v, d);
+        const bool               valid = (mask >> ((threadIdx.x & 31u) ^ static_cast<unsigned>(d))) & 1u;
+        if (valid && other > v) v = other;
+    }
+    return v;
+}
+
+// ---- the whole build as ONE persistent launch ---------------------------------------------------------------------
+// The level-by-level path above costs ~10 launches and one host read-back per level (~50 levels for Sponza: 5.4 ms, nearly
+// all of it launch latency and synchronisation).  Here every phase is a grid-stride loop of the same device functions inside
+// one kernel whose blocks are all resident, separated by a grid-wide barrier (~2 us instead of a launch boundary), and the
+// level bookkeeping stays on the device.  The partition's scan is done in place: every block scans its contiguous slice of
+// the flags, the slice totals (one per block) are summed by each block for itself.
+struct FusedControl
+{
+    unsigned int  barrier;      // grid barrier: arrivals so far (monotonic)
+    std::uint32_t numLevels;    // levels built
+    std::uint32_t numNodes;
+    std::uint32_t error;        // 1: more than MAX_LEVELS levels
+    unsigned long long phaseNs[12]; // time block 0 spent in each phase incl. its barrier (diagnostics): boxes, decide, buckets, sweep, scan, offsets, pair,
+                                    // permute, level bookkeeping, numbering, emit
+};
+constexpr std::uint32_t FUSED_MAX_LEVELS = 4096;
+
+__device__ __forceinline__ void gridBarrier(FusedControl* ctl, unsigned int& generation)
+{
+    __syncthreads();
+    ++generation;
+    if (threadIdx.x == 0)
+    {
+        __threadfence(); // this block's writes before its arrival
+        atomicAdd(&ctl->barrier, 1u);
+        const unsigned int target = generation * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned int*>(&ctl->barrier) < target) {}
+        __threadfence(); // (also invalidates this SM's L1: the other blocks' writes are read from L2)
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
+    const rf_positions* __restrict__ tris, const std::uint32_t n, Prim* prims, std::uint32_t* order0, std::uint32_t* order1, std::uint32_t* owner,
+    std::uint32_t* slotLeft, std::uint32_t* slotRight, std::uint32_t* counters, BuildNode* nodes, NodeAccum* accum, BucketAccum* buckets,
+    unsigned long long* flags, unsigned long long* scan, unsigned long long* blockTotals, std::uint32_t* levelStart, FusedControl* ctl, rf_bvh_node* out,
+    unsigned long long* triangleIndices)
+{
+    __shared__ unsigned long long warpSums[BUILD_THREADS / 32];
+    __shared__ unsigned long long sliceCarry;
+    __shared__ BucketAccum        blockBuckets;
+    __shared__ NodeAccum          blockAccum;
+    unsigned int        generation = 0;
+    const std::uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    unsigned long long  phaseStart = 0;
+    const auto          now = []() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
+    const auto endPhase = [&](const int phase) { // barrier + bookkeeping of the phase's duration as block 0 sees it
+        gridBarrier(ctl, generation);
+        if (tid == 0)
+        {
+            const unsigned long long t = now();
+            ctl->phaseNs[phase] += t - phaseStart;
+            phaseStart = t;
+        }
+    };
+    const std::uint32_t nPadded = (n + 31u) & ~31u;
+
+    // primitives and the root (k_bvh_prims, k_bvh_root)
+    for (std::uint32_t i = tid; i < n; i += stride)
+    {
+        const rf_positions t = tris[i];
+        const V3           p0 = v3(t.v0), p1 = v3(t.v1), p2 = v3(t.v2);
+        const Box          box = makeBox(vmin(vmin(p0, p1), p2), vmax(vmax(p0, p1), p2));
+        const V3           c = 0.5f * (box.lo + box.hi);
+        prims[i] = Prim{make_float4(box.lo.x, box.lo.y, box.lo.z, c.x), make_float4(box.hi.x, box.hi.y, box.hi.z, c.y), c.z};
+        order0[i] = i;
+        owner[i] = 0u;
+    }
+    if (tid == 0)
+    {
+        BuildNode root{};
+        root.begin = 0u, root.end = n, root.kind = KIND_OPEN, root.child0 = NONE, root.child1 = NONE;
+        nodes[0] = root;
+        resetAccum(accum[0]);
+        counters[0] = 1u, counters[1] = 0u;
+        levelStart[0] = 0u;
+    }
+    gridBarrier(ctl, generation);
+    if (tid == 0) phaseStart = now();
+
+    std::uint32_t  levelBegin = 0, levelEnd = 1, level = 0;
+    std::uint32_t* order = order0;
+    std::uint32_t* orderNext = order1;
+    // contiguous slice of the positions [0, n] (n + 1 flags: the last one is the scan's total) every block scans
+    const std::uint32_t slice = (n + 1u + gridDim.x - 1u) / gridDim.x;
+    const std::uint32_t sliceBegin = min(blockIdx.x * slice, n + 1u), sliceEnd = min(sliceBegin + slice, n + 1u);
+    while (levelBegin != levelEnd)
+    {
+        // boxes (same remark as for the buckets below: a round that lies in one node is folded in shared memory first)
+        for (std::uint32_t base = blockIdx.x * BUILD_THREADS; base < nPadded; base += stride)
+        {
+            const std::uint32_t i = base + threadIdx.x;
+            const std::uint32_t node = i < n ? owner[i] : NONE;
+            const std::uint32_t first = owner[min(base, n - 1u)];
+            const int           uniform = __syncthreads_and((i >= n || node == first) ? 1 : 0) && first != NONE;
+            if (!uniform)
+            {
+                boxesAt(i, n, prims, order, owner, accum);
+                continue;
+            }
+            if (threadIdx.x == 0) resetAccum(blockAccum);
+            __syncthreads();
+            if (i < n)
+            {
+                const Prim p = prims[order[i]];
+                for (int k = 0; k < 3; ++k)
+                {
+                    unsigned long long lo = loKey(comp(p.lo, k), i), hi = hiKey(comp(p.hi, k), i);
+                    std::uint32_t      cl = orderedBits(centroidOf(p, k)), ch = cl;
+                    const unsigned     mask = __activemask();
+                    lo = __reduce_min_sync_u64(mask, lo), hi = __reduce_max_sync_u64(mask, hi);
+                    cl = __reduce_min_sync(mask, cl), ch = __reduce_max_sync(mask, ch);
+                    if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(static_cast<int>(mask)) - 1))
+                    {
+                        atomicMin(&blockAccum.boxLo[k], lo);
+                        atomicMax(&blockAccum.boxHi[k], hi);
+                        atomicMin(&blockAccum.centLo[k], cl);
+                        atomicMax(&blockAccum.centHi[k], ch);
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 3)
+            {
+                NodeAccum& a = accum[first];
+                atomicMin(&a.boxLo[threadIdx.x], blockAccum.boxLo[threadIdx.x]);
+                atomicMax(&a.boxHi[threadIdx.x], blockAccum.boxHi[threadIdx.x]);
+                atomicMin(&a.centLo[threadIdx.x], blockAccum.centLo[threadIdx.x]);
+                atomicMax(&a.centHi[threadIdx.x], blockAccum.centHi[threadIdx.x]);
+            }
+            __syncthreads();
+        }
+        endPhase(0);
+        for (std::uint32_t s = levelBegin + tid; s < levelEnd; s += stride) decideAt(s, nodes, accum, buckets, prims, order, owner, counters);
+        endPhase(1);
+        // buckets.  The 256 consecutive positions a block handles per round mostly lie in ONE node while nodes are large, and
+        // then all 256 threads would hammer the same 84 accumulator words in L2 (measured: 2.4 of 5.3 ms for Sponza): such a
+        // round is folded in shared memory first and leaves with one atomic per word.
+        for (std::uint32_t base = blockIdx.x * BUILD_THREADS; base < n; base += stride)
+        {
+            const std::uint32_t i = base + threadIdx.x;
+            const std::uint32_t node = i < n ? owner[i] : NONE;
+            const std::uint32_t first = owner[base];
+            const bool          sahHere = node != NONE && nodes[node].kind == KIND_SAH;
+            const int           uniform = __syncthreads_and((i >= n || node == first) ? 1 : 0) && first != NONE;
+            if (!uniform)
+            {
+                if (i < n) bucketsAt(i, prims, order, owner, nodes, buckets);
+                continue;
+            }
+            if (nodes[first].kind != KIND_SAH) continue; // (uniform for the block: `first` is)
+            for (std::uint32_t k = threadIdx.x; k < BVH_NUM_BUCKETS; k += BUILD_THREADS)
+            {
+                blockBuckets.count[k] = 0u;
+                for (int c = 0; c < 3; ++c) blockBuckets.lo[k][c] = 0xFFFFFFFFu, blockBuckets.hi[k][c] = 0u;
+            }
+            __syncthreads();
+            if (sahHere)
+            {
+                const BuildNode&  nd = nodes[node];
+                const Prim        p = prims[order[i]];
+                const std::size_t b = bvhBucketOf(centroidOf(p, nd.axis), nd.cLo, nd.cHi);
+                atomicAdd(&blockBuckets.count[b], 1u);
+                for (int k = 0; k < 3; ++k)
+                {
+                    atomicMin(&blockBuckets.lo[b][k], orderedBits(comp(p.lo, k)));
+                    atomicMax(&blockBuckets.hi[b][k], orderedBits(comp(p.hi, k)));
+                }
+            }
+            __syncthreads();
+            BucketAccum& acc = buckets[nodes[first].bucketSlot];
+            for (std::uint32_t k = threadIdx.x; k < BVH_NUM_BUCKETS; k += BUILD_THREADS)
+            {
+                if (blockBuckets.count[k] == 0u) continue;
+                atomicAdd(&acc.count[k], blockBuckets.count[k]);
+                for (int c = 0; c < 3; ++c)
+                {
+                    atomicMin(&acc.lo[k][c], blockBuckets.lo[k][c]);
+                    atomicMax(&acc.hi[k][c], blockBuckets.hi[k][c]);
+                }
+            }
+            __syncthreads();
+        }
+        endPhase(2);
+        for (std::uint32_t s = levelBegin + tid; s < levelEnd; s += stride) sweepAt(s, nodes, accum, buckets, owner, counters);
+        endPhase(3);
+        // flags + exclusive scan of this block's slice (relative to the slice), slice total
+        if (threadIdx.x == 0) sliceCarry = 0ull;
+        __syncthreads();
+        for (std::uint32_t base = sliceBegin; base < sliceEnd; base += BUILD_THREADS)
+        {
+            const std::uint32_t      i = base + threadIdx.x;
+            const unsigned long long f = i < sliceEnd ? flagAt(i, n, prims, order, owner, nodes) : 0ull;
+            // inclusive scan of the tile: within the warp, then across the warps (both halves of f are < 2^32: no carries cross)
+            unsigned long long incl = f;
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((threadIdx.x & 31u) >= static_cast<unsigned>(d)) incl += up;
+            }
+            if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            unsigned long long before = sliceCarry;
+            for (std::uint32_t wIdx = 0; wIdx < (threadIdx.x >> 5); ++wIdx) before += warpSums[wIdx];
+            if (i < sliceEnd)
+            {
+                flags[i] = f;
+                scan[i] = before + incl - f;
+            }
+            __syncthreads();
+            if (threadIdx.x == BUILD_THREADS - 1) sliceCarry = before + incl;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) blockTotals[blockIdx.x] = sliceCarry;
+        endPhase(4);
+        // offset of the slice = totals of the slices before it; make the scan global
+        {
+            unsigned long long mine = 0ull;
+            for (std::uint32_t b = threadIdx.x; b < blockIdx.x; b += BUILD_THREADS) mine += blockTotals[b];
+            for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+            if ((threadIdx.x & 31u) == 0u) warpSums[threadIdx.x >> 5] = mine;
+            __syncthreads();
+            unsigned long long offset = 0ull;
+            for (int wIdx = 0; wIdx < BUILD_THREADS / 32; ++wIdx) offset += warpSums[wIdx];
+            for (std::uint32_t i = sliceBegin + threadIdx.x; i < sliceEnd; i += BUILD_THREADS) scan[i] += offset;
+        }
+        endPhase(5);
+        for (std::uint32_t i = tid; i < n; i += stride) pairAt(i, owner, nodes, flags, scan, slotLeft, slotRight);
+        endPhase(6);
+        for (std::uint32_t i = tid; i < n; i += stride) permuteAt(i, owner, nodes, flags, scan, slotLeft, slotRight, order, orderNext);
+        {
+            std::uint32_t* t = order;
+            order = orderNext, orderNext = t;
+        }
+        endPhase(7);
+        // next level: the node slots created by this one
+        const std::uint32_t created = *reinterpret_cast<volatile std::uint32_t*>(&counters[0]);
+        ++level;
+        if (tid == 0)
+        {
+            if (level < FUSED_MAX_LEVELS) levelStart[level] = levelEnd;
+            counters[1] = 0u; // bucket slots of the next level
+        }
+        levelBegin = levelEnd, levelEnd = created;
+        if (level >= FUSED_MAX_LEVELS - 1u)
+        {
+            if (tid == 0) ctl->error = 1u;
+            break;
+        }
+        endPhase(8);
+    }
+    if (tid == 0) ctl->numLevels = level, ctl->numNodes = levelEnd;
+    const std::uint32_t numNodes = levelEnd;
+    gridBarrier(ctl, generation);
+    if (tid == 0) phaseStart = now();
+    // numbering: sizes bottom-up, pre-order top-down, records
+    for (std::uint32_t l = level; l-- > 0u;)
+    {
+        const std::uint32_t b = levelStart[l], e = l + 1u < level ? levelStart[l + 1u] : numNodes;
+        for (std::uint32_t s = b + tid; s < e; s += stride) sizeAt(s, nodes);
+        gridBarrier(ctl, generation);
+    }
+    for (std::uint32_t l = 0; l < level; ++l)
+    {
+        const std::uint32_t b = levelStart[l], e = l + 1u < level ? levelStart[l + 1u] : numNodes;
+        for (std::uint32_t s = b + tid; s < e; s += stride) preorderAt(s, nodes);
+        gridBarrier(ctl, generation);
+    }
+    if (tid == 0)
+    {
+        const unsigned long long t = now();
+        ctl->phaseNs[9] += t - phaseStart;
+        phaseStart = t;
+    }
+    for (std::uint32_t s = tid; s < numNodes; s += stride) emitAt(s, nodes, out);
+    for (std::uint32_t i = tid; i < n; i += stride) triangleIndices[order[i]] = i; // bvh.cpp:64-69
+    if (tid == 0) ctl->phaseNs[10] += now() - phaseStart;
 }
 
 template<typename T>
@@ -439,6 +783,22 @@ inline unsigned gridOf(std::uint64_t items) { return static_cast<unsigned>((item
 } // namespace rfb200
 
 using namespace rfb200;
+
+namespace
+{
+float g_lastPhaseMs[12] = {};
+std::uint32_t g_lastLevels = 0;
+bool g_levelKernels = false; // rf_build_bvh_device_set_mode(1): the level-by-level path (one launch per phase and level), kept for A/B timing
+}
+extern "C" void rf_build_bvh_device_set_mode(std::int32_t levelKernels) { g_levelKernels = levelKernels != 0; }
+// Diagnostics of the last single-launch build: milliseconds block 0 spent in each phase (summed over the levels) and the
+// number of levels.  out_phase_ms has 12 entries: boxes, decide, buckets, sweep, scan, offsets, pair, permute, level
+// bookkeeping, numbering, emit, unused.
+extern "C" std::uint32_t rf_build_bvh_device_last_phases(float* outPhaseMs)
+{
+    if (outPhaseMs) std::memcpy(outPhaseMs, g_lastPhaseMs, sizeof(g_lastPhaseMs));
+    return g_lastLevels;
+}
 
 #define RF_BUILD_CUDA(expr)                                                                                              \
     do                                                                                                                   \
@@ -502,6 +862,45 @@ extern "C" rf_status rf_build_bvh_device(
     cudaEvent_t evBegin = nullptr, evEnd = nullptr;
     RF_BUILD_CUDA(cudaEventCreate(&evBegin));
     RF_BUILD_CUDA(cudaEventCreate(&evEnd));
+
+    if (!g_levelKernels)
+    {
+        // one persistent launch: as many blocks as are resident together (the grid barrier needs all of them running)
+        int currentDevice = 0, numSms = 0, blocksPerSm = 0;
+        RF_BUILD_CUDA(cudaGetDevice(&currentDevice));
+        RF_BUILD_CUDA(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, currentDevice));
+        RF_BUILD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, k_bvh_build_fused, BUILD_THREADS, 0));
+        if (blocksPerSm < 1) return setError(RF_ERROR_CUDA, "rf_build_bvh_device: the build kernel does not fit an SM");
+        const int                grid = numSms * std::min(blocksPerSm, 2);
+        Buf<unsigned long long>  blockTotals;
+        Buf<std::uint32_t>       levelStartDev;
+        Buf<FusedControl>        control;
+        RF_BUILD_CUDA(blockTotals.allocate(static_cast<std::size_t>(grid)));
+        RF_BUILD_CUDA(levelStartDev.allocate(FUSED_MAX_LEVELS));
+        RF_BUILD_CUDA(control.allocate(1));
+        RF_BUILD_CUDA(cudaMemset(control.ptr, 0, sizeof(FusedControl)));
+        RF_BUILD_CUDA(cudaEventRecord(evBegin));
+        k_bvh_build_fused<<<grid, BUILD_THREADS>>>(dTris.ptr, n, prims.ptr, order[0].ptr, order[1].ptr, owner.ptr, slotLeft.ptr, slotRight.ptr, counters.ptr,
+                                                   nodes.ptr, accum.ptr, buckets.ptr, flags.ptr, scan.ptr, blockTotals.ptr, levelStartDev.ptr, control.ptr,
+                                                   dOut.ptr, dIndices.ptr);
+        RF_BUILD_CUDA(cudaEventRecord(evEnd));
+        RF_BUILD_CUDA(cudaEventSynchronize(evEnd));
+        RF_BUILD_CUDA(cudaGetLastError());
+        FusedControl result{};
+        RF_BUILD_CUDA(cudaMemcpy(&result, control.ptr, sizeof(result), cudaMemcpyDeviceToHost));
+        if (result.error != 0u || result.numNodes > maxNodes) return setError(RF_ERROR_CUDA, "rf_build_bvh_device: the tree has too many levels (internal limit)");
+        float fusedMs = 0.f;
+        cudaEventElapsedTime(&fusedMs, evBegin, evEnd);
+        cudaEventDestroy(evBegin), cudaEventDestroy(evEnd);
+        if (out_device_ms) *out_device_ms = fusedMs;
+        for (int k = 0; k < 12; ++k) g_lastPhaseMs[k] = static_cast<float>(result.phaseNs[k]) * 1e-6f;
+        g_lastLevels = result.numLevels;
+        RF_BUILD_CUDA(cudaMemcpy(out_nodes, dOut.ptr, result.numNodes * sizeof(rf_bvh_node), cudaMemcpyDeviceToHost));
+        RF_BUILD_CUDA(cudaMemcpy(out_triangle_indices, dIndices.ptr, n * sizeof(std::uint64_t), cudaMemcpyDeviceToHost));
+        *out_num_nodes = result.numNodes;
+        return RF_OK;
+    }
+
     RF_BUILD_CUDA(cudaEventRecord(evBegin));
 
     k_bvh_prims<<<gridOf(n), BUILD_THREADS>>>(dTris.ptr, n, prims.ptr, order[0].ptr, owner.ptr);
