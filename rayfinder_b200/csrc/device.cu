@@ -228,19 +228,42 @@ void launchTracePairs(int variant, int grid, cudaStream_t s, Args&&... args)
     }
 }
 
-template<typename... Args>
-void launchMega(int variant, int block, int grid, cudaStream_t s, Args&&... args)
+// The persistent kernel (mega.cuh) with the stack the scene needs, like launchTrace; blocks of 256 threads (4 per SM, 7
+// traversal warps + 1 shading warp each) or 512 threads (2 per SM, 15 + 1).
+template<int V, int BLOCK, int STACK, typename... Args>
+void launchMegaV(int grid, cudaStream_t s, Args&&... args)
 {
-    if (block == 64)
-        k_mega<TRACE_DEFAULT_VARIANT, 64><<<grid, 64, 0, s>>>(args...);
-    else if (block == 128)
-        k_mega<TRACE_DEFAULT_VARIANT, 128><<<grid, 128, 0, s>>>(args...);
+    constexpr std::size_t bytes = megaSharedBytes<BLOCK, STACK>();
+    static bool           configured = false; // (per instantiation; the attribute is per device function, set again after a device change is harmless)
+    if (!configured)
+    {
+        cudaFuncSetAttribute(k_mega<V, BLOCK, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+        configured = true;
+    }
+    k_mega<V, BLOCK, STACK><<<grid, BLOCK, bytes, s>>>(args...);
+}
+template<typename... Args>
+void launchMega(int variant, int block, std::uint32_t stackEntries, int grid, cudaStream_t s, Args&&... args)
+{
+    if (block == 512)
+    {
+        if (stackEntries <= 23u)
+            launchMegaV<TRACE_DEFAULT_VARIANT, 512, 23>(grid, s, args...);
+        else if (stackEntries <= 31u)
+            launchMegaV<TRACE_DEFAULT_VARIANT, 512, 31>(grid, s, args...);
+        else
+            launchMegaV<TRACE_DEFAULT_VARIANT, 512, RF_STACK_SIZE>(grid, s, args...);
+    }
     else if ((variant & 15) == 2)
-        k_mega<2, 256><<<grid, 256, 0, s>>>(args...);
+        launchMegaV<2, 256, RF_STACK_SIZE>(grid, s, args...);
     else if ((variant & 15) == 1)
-        k_mega<1, 256><<<grid, 256, 0, s>>>(args...);
+        launchMegaV<1, 256, RF_STACK_SIZE>(grid, s, args...);
+    else if (stackEntries <= 23u)
+        launchMegaV<TRACE_DEFAULT_VARIANT, 256, 23>(grid, s, args...);
+    else if (stackEntries <= 31u)
+        launchMegaV<TRACE_DEFAULT_VARIANT, 256, 31>(grid, s, args...);
     else
-        k_mega<TRACE_DEFAULT_VARIANT, 256><<<grid, 256, 0, s>>>(args...);
+        launchMegaV<TRACE_DEFAULT_VARIANT, 256, RF_STACK_SIZE>(grid, s, args...);
 }
 
 // =================================================================================================
@@ -288,9 +311,8 @@ struct rf_renderer
         DeviceBuffer<std::uint32_t> ownedTiles;
         DeviceBuffer<std::uint32_t> counters; // see counterSlots()
         DeviceBuffer<StragglerRecord> stragglers; // rays handed over by the tails of the traversal launches (traversal.cuh)
-        DeviceBuffer<std::uint32_t> meta, ready; // persistent-kernel mode: path meta, ready ring (mega.cuh)
-        DeviceBuffer<MegaControl>   control;
-        std::uint32_t               log2Cap = 0;
+        DeviceBuffer<float4>        pathRecords; // persistent-kernel mode: blocks x slots path records (mega.cuh), allocated on first use
+        std::uint64_t               pathRecordSlots = 0;
         PathQueue                   queues[2]{};
         std::uint64_t               capacity = 0; // paths
         std::uint32_t               numOwnedTiles = 0;
@@ -328,7 +350,7 @@ struct rf_renderer
     std::uint64_t kernelLaunches = 0;   // kernels launched by render() since the last reset_stats
     int         numSubFrames = 2;       // in effect (updateTiles)
     int         requestedSubFrames = 0; // 0: automatic
-    bool        megakernel = false; // experimental: the frame as one persistent kernel (mega.cuh); slower so far
+    bool        megakernel = false; // the frame as one persistent kernel with block-local path loops (mega.cuh)
     cudaEvent_t forkEvent = nullptr;
 
     rf_render_parameters params{};
@@ -480,12 +502,6 @@ struct rf_renderer
                 RF_CUDA(sf.ownedTiles.allocate(sf.numOwnedTiles));
                 if (!sf.counters.ptr) RF_CUDA(sf.counters.allocate(counterSlots(1024)));
                 if (!sf.stragglers.ptr) RF_CUDA(sf.stragglers.allocate(stragglerCapacity()));
-                if (!sf.control.ptr) RF_CUDA(sf.control.allocate(1));
-                sf.log2Cap = 0;
-                while ((1ull << sf.log2Cap) < need) ++sf.log2Cap;
-                if (sf.log2Cap > RING_ID_BITS) return setError(RF_ERROR_INVALID_ARGUMENT, "Framebuffer too large for one sub-frame.");
-                RF_CUDA(sf.meta.allocate(need));
-                RF_CUDA(sf.ready.allocate(1ull << sf.log2Cap));
                 for (int q = 0; q < 2; ++q)
                 {
                     float4* base = sf.queueMem.ptr + static_cast<std::uint64_t>(q) * 4 * need;
@@ -519,7 +535,9 @@ struct rf_renderer
     std::uint32_t forcedStackEntries = 0;
     std::uint32_t traceStackEntries() const { return std::max(forcedStackEntries, stackEntries); }
     std::uint32_t evictDelay = 4; // rounds a warp keeps its last rays before handing them over (measured: 4 lets the many short ones end in place)
-    bool          stageDebug = false, megaDebug = false;
+    bool          stageDebug = false;
+    std::uint32_t megaSlots = 0; // path slots per block of the persistent kernel (0: automatic; option "mega_slots")
+    int           megaBlock = 256; // threads per block of the persistent kernel (256 or 512; option "mega_block")
     int           stragglerWindowMode = STRAGGLER_DIRECT; // how the tail kernel fetches its node windows (straggler.cuh)
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
@@ -762,24 +780,25 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         std::uint32_t* const cursors = ctr + fp.numBounces + 1u;
         if (r->megakernel && !staged)
         {
-            RF_CUDA(cudaMemsetAsync(sf.ready.ptr, 0, (1ull << sf.log2Cap) * sizeof(std::uint32_t), ss));
-            k_raygen_mega<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, scene, sf.ownedTiles.ptr, sf.queues[0], sf.meta.ptr, sf.ready.ptr, sf.log2Cap, &ctr[0],
-                                                              r->radiance.ptr, r->stats.ptr);
-            k_mega_init<<<1, 1, 0, ss>>>(sf.control.ptr, &ctr[0]);
-            launchMega(r->variant, r->traceBlock, gridTrace, ss, sfp, scene, sf.queues[0], sf.meta.ptr, r->radiance.ptr, sf.control.ptr, sf.ready.ptr,
-                       sf.log2Cap, r->stats.ptr);
-            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, exchangeTarget, restart);
-            r->kernelLaunches += 4;
-            if (r->megaDebug)
+            // One launch for the tile set's whole frame (mega.cuh): all SM slots divided among the tile sets, and as many path
+            // slots per block as the block's share of the pixels needs (every path in flight from the start: the paths of a
+            // block then advance together and end together), at most loopMaxSlots().
+            const int           megaGrid = r->gridFor(r->traceBlocksPerSm > 0 ? r->traceBlocksPerSm : std::max(1, 4 / r->numSubFrames)) * 256 / r->megaBlock;
+            const std::uint64_t pathsPerBlock = (static_cast<std::uint64_t>(sf.numOwnedTiles) * TILE_PIXELS + megaGrid - 1) / megaGrid;
+            const std::uint32_t maxSlots = loopMaxSlots(r->megaBlock);
+            const std::uint32_t slots = r->megaSlots != 0u ? std::min(r->megaSlots, maxSlots)
+                                                           : static_cast<std::uint32_t>(std::min<std::uint64_t>(maxSlots, std::max<std::uint64_t>(r->megaBlock, (pathsPerBlock + 31u) & ~31ull)));
+            const std::uint64_t recordSlots = static_cast<std::uint64_t>(megaGrid) * slots;
+            if (recordSlots > sf.pathRecordSlots)
             {
-                MegaControl   c{};
-                std::uint32_t n = 0;
-                cudaStreamSynchronize(ss);
-                cudaMemcpy(&c, sf.control.ptr, sizeof(c), cudaMemcpyDeviceToHost);
-                cudaMemcpy(&n, &ctr[0], sizeof(n), cudaMemcpyDeviceToHost);
-                std::fprintf(stderr, "[mega] sub-frame %d: paths %u head %u tail %u avail %d live 0x%x log2Cap %u (%s)\n", i, n, c.head, c.tail, c.avail,
-                             c.live, sf.log2Cap, cudaGetErrorString(cudaGetLastError()));
+                RF_CUDA(cudaStreamSynchronize(ss));
+                RF_CUDA(sf.pathRecords.allocate(recordSlots * LOOP_RECORD_VEC));
+                sf.pathRecordSlots = recordSlots;
             }
+            launchMega(r->variant, r->megaBlock, r->traceStackEntries(), megaGrid, ss, sfp, scene, sf.ownedTiles.ptr, sf.pathRecords.ptr, slots, r->radiance.ptr, &ctr[0],
+                       reinterpret_cast<std::uint32_t*>(r->stats.ptr + STAT_FAILED), r->stats.ptr);
+            k_accumulate<<<gridLight, BLOCK_THREADS, 0, ss>>>(sfp, sf.ownedTiles.ptr, r->radiance.ptr, r->image.ptr, exchangeTarget, restart);
+            r->kernelLaunches += 2;
             if (i > 0)
             {
                 RF_CUDA(cudaEventRecord(sf.done, ss));
@@ -1096,6 +1115,7 @@ extern "C" rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out)
     out->evict_max = r->megakernel ? 0u : r->effectiveEvictMax();
     out->node_records_loaded = s[STAT_RECORDS];
     out->trace_kernel = r->usePairs() && !r->megakernel ? 2u : 1u;
+    if (s[STAT_FAILED] != 0ull) return setError(RF_ERROR_CUDA, "The persistent kernel left a frame on its watchdog (a lost path); the image is incomplete.");
     return RF_OK;
 }
 
@@ -1140,7 +1160,17 @@ extern "C" int rf_debug_timeline_arm(std::uint32_t capacity)
     cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf));
     cudaMemcpyToSymbol(g_timelineCount, &zero, sizeof(zero));
     cudaMemcpyToSymbol(g_timelineCap, &capacity, sizeof(capacity));
+    static const unsigned long long zeros[OCC_BUCKETS] = {};
+    cudaMemcpyToSymbol(g_occBusy, zeros, sizeof(zeros));
+    cudaMemcpyToSymbol(g_occRounds, zeros, sizeof(zeros));
     return cudaDeviceSynchronize() != cudaSuccess;
+}
+// busy[256] then rounds[256]: lane occupancy of the traversal warps per 16.4 us bucket of %globaltimer (traversal.cuh)
+extern "C" void rf_debug_occupancy_read(unsigned long long* dst)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(dst, g_occBusy, sizeof(unsigned long long) * OCC_BUCKETS);
+    cudaMemcpyFromSymbol(dst + OCC_BUCKETS, g_occRounds, sizeof(unsigned long long) * OCC_BUCKETS);
 }
 extern "C" std::uint32_t rf_debug_timeline_read(void* dst, std::uint32_t capacity)
 {
@@ -1228,7 +1258,8 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
     else if (key == "pair_variant" && value <= 7) r->pairVariant = static_cast<int>(value);
     else if (key == "tail_window_mode" && value <= 1) r->stragglerWindowMode = static_cast<int>(value);
     else if (key == "stage_debug") r->stageDebug = value != 0;
-    else if (key == "mega_debug") r->megaDebug = value != 0;
+    else if (key == "mega_slots" && (value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0))) r->megaSlots = static_cast<std::uint32_t>(value);
+    else if (key == "mega_block" && (value == 256 || value == 512)) r->megaBlock = static_cast<int>(value);
     else return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: unknown option '%s'", name);
     return RF_OK;
 }

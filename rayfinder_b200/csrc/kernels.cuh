@@ -83,6 +83,7 @@ enum StatSlot
     STAT_SHADOW_NODES,
     STAT_SHADOW_TRIS,
     STAT_RECORDS, // BVH records loaded by the traversal kernels (pair records, or nodes with the per-node kernel)
+    STAT_FAILED,  // low word set to 1 by the persistent kernel's watchdog (mega.cuh)
     STAT_COUNT
 };
 
@@ -237,6 +238,7 @@ __device__ __forceinline__ V3 skyForMiss(const FrameParams& fp, const V3 v, cons
 struct SurfaceShade
 {
     V3 p, wi, nextThroughput, contribution;
+    V3 lightDir; // the pixel's sun sample (= sunSampleDirection): direction of the shadow ray from p
 };
 __device__ __forceinline__ SurfaceShade shadeSurfaceHit(
     const FrameParams& fp, const SceneDevice& scene, const HitRecord& hit, const std::uint32_t idx, const V3 throughput, const V3 sunDir)
@@ -277,6 +279,7 @@ __device__ __forceinline__ SurfaceShade shadeSurfaceHit(
     const float cosTheta = 1.0f - ux * (1.0f - fp.solarCosThetaMax);
     const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
     const V3    lightDir = onbTransform(sunDir, v3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+    out.lightDir = lightDir;
 
     // rayColor hit branch, wgsl:191-203.
     const float FRAC_1_PI = 0.31830987f;

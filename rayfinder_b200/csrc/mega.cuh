@@ -1,243 +1,181 @@
-// The frame as ONE persistent kernel: the stages of kernels.cuh (traversal, shading + sky, compaction of live
-// paths) run inside a single launch and hand paths to each other through device queues instead of kernel
-// boundaries.
+// The frame as ONE persistent kernel with BLOCK-LOCAL path loops: ray generation, traversal, shading + sky and the
+// compaction of live paths all run inside a single launch, and a path never leaves the block that generated it.
 //
-// Why: a traversal launch cannot end before its longest ray has walked its ~10^3 nodes one after the other
-// (a latency floor of ~0.25 ms per launch on B200, measured), and the staged pipeline pays that floor 9 times
-// per 8-bounce frame — 2.2 ms, which is what caps multi-GPU strong scaling.  Here the floor is paid once per
-// frame: while a few lanes finish long rays, the other lanes shade and trace paths of any bounce.
+// Why: a traversal launch cannot end before its longest ray has walked its ~10^3 nodes one after the other, and at the
+// share one GPU has of a 1080p frame split over 8 GPUs (260 k paths on 151 k resident lanes) every one of the staged
+// pipeline's nine traversal launches is mostly that drain.  Here nothing waits for a bounce to finish: a lane that ends a
+// ray takes whatever ray of whatever bounce is ready next in its block.
 //
-//   work item      = a path that has a ray to trace: (shadow ray of its last hit, then) its next closest-hit ray,
-//                    both on the same lane, so the per-pixel order of `radiance +=` is the reference's
-//                    (direct light of bounce b before anything of bounce b + 1)
-//   ready ring     = device ring buffer of path ids; producers reserve with atomicAdd(tail), consumers with a
-//                    counting semaphore (`avail`) + atomicAdd(head); entries carry a lap tag so a consumer can
-//                    tell a published entry from a stale one without anyone resetting slots
-//   shade batch    = warp specialisation: in every block all warps but one only trace; they hand the paths whose
-//                    closest-hit ray they finished to the block's shading warp through a shared-memory ring, and
-//                    that warp shades 32 of them at a time (dense: one path per lane), appending the survivors
-//                    to the ready ring — this is the stream compaction of live paths
-//   termination    = `live` counts paths that have not ended; a warp that runs dry reports the paths it ended and
-//                    leaves when live == 0
+// Round 1's version of this kernel passed paths between blocks through a device-wide ring (a semaphore, head / tail
+// counters and lap-tagged entries in global memory) and paid three to four dependent L2 round trips per ray for it; it
+// never caught up with the staged pipeline.  This one has NO global synchronisation on the path of a ray:
 //
-// Path state is written by one warp and read by another without a kernel boundary in between, so every access
-// to it (and to the per-frame radiance buffer) goes through L2 (`ld.global.cg`): L1 is not coherent across SMs.
+//   block          = 7 traversal warps (traceRays with PathLoopIO) + 1 shading warp
+//   path record    = 96 B in global memory (L2-resident), in a region that belongs to the block: written only by the block's
+//                    shading warp, read by its traversal lanes with ONE round trip per ray (origin + the direction to trace)
+//   ready ring     = shared memory, single producer (the shading warp), consumers reserve with one shared-memory CAS per
+//                    warp refill; FIFO, so the paths of a block advance together and end together
+//   hit ring       = shared memory, the traversal lanes' finished closest-hit rays on their way to the shading warp, which
+//                    shades 32 of them at a time (one path per lane) — this is the stream compaction of live paths
+//   shadow rays    = traced by the lane that then traces the path's next closest-hit ray (same origin; one 16-byte load for
+//                    the new direction); the lane carries the shadow result as one bit, and the shading warp folds
+//                    `radiance += contribution * visibility * invPdf` (rayColor:203) into the path's next shading step —
+//                    before anything of the next bounce is added, i.e. in the reference's order.  Radiance lives in the
+//                    path record and is written to the frame's buffer once, when the path ends
+//   new paths      = the shading warp takes 32 pixels at a time from the frame's cursor (the only global atomic: one per 32
+//                    paths) whenever 32 path slots are free, so blocks whose paths are short simply take more pixels
+//   termination    = per block: cursor dry and every slot free
 #pragma once
 
 #include "kernels.cuh"
 
 namespace rfb200
 {
-struct MegaControl
-{
-    std::uint32_t head;  // next ring position to consume
-    std::uint32_t tail;  // next ring position to produce
-    int           avail; // published - reserved entries (may dip below 0 transiently)
-    std::uint32_t live;  // paths that have not ended
-};
+// Per block of BLOCK threads: up to 2 x BLOCK path slots (the launch picks how many are used), ready rings of the same
+// capacity (so they can never overflow), a hit ring of BLOCK / 2 entries (every KB of shared memory is a KB less L1).
+__host__ __device__ constexpr std::uint32_t loopMaxSlots(const int block) { return 2u * static_cast<std::uint32_t>(block); }
+constexpr std::uint32_t LOOP_LEVELS = 16;       // bounce levels told apart by the scheduling priority (deeper ones share the last)
+constexpr std::uint32_t LOOP_RECORD_VEC = 6;    // float4 per path record
 
-constexpr std::uint32_t META_BOUNCE_MASK = 0xFFFFu; // bounce number of the path's next closest-hit ray (1-based)
-constexpr std::uint32_t META_DO_CLOSEST = 1u << 16;
-constexpr std::uint32_t META_DO_SHADOW = 1u << 17;
-constexpr std::uint32_t RING_ID_BITS = 26; // up to 2^26 paths per sub-frame; 6 bits of lap tag
-constexpr std::uint32_t RING_ID_MASK = (1u << RING_ID_BITS) - 1u;
+// path record, float4 index
+constexpr int REC_ORIGIN = 0;       // ray origin xyz, w = number of the path's next closest-hit ray (1-based, bits)
+constexpr int REC_SHADOW_DIR = 1;   // direction of the shadow ray from that origin (the pixel's sun sample), w = pixel index (bits)
+constexpr int REC_NEXT_DIR = 2;     // direction of the next closest-hit ray
+constexpr int REC_THROUGHPUT = 3;
+constexpr int REC_CONTRIBUTION = 4; // throughput * lightIntensity * reflectance of the last hit (NEE term without visibility)
+constexpr int REC_RADIANCE = 5;
 
-__device__ __forceinline__ std::uint32_t ringEntry(const std::uint32_t pos, const std::uint32_t log2Cap, const std::uint32_t id)
-{
-    return ((((pos >> log2Cap) + 1u) & 63u) << RING_ID_BITS) | id;
-}
-
-__device__ __forceinline__ float4 ldcg4(const float4* p) { return __ldcg(p); }
-
-// Ray generation for the persistent kernel: k_raygen + the initial ring entries and path meta.
-__global__ void __launch_bounds__(BLOCK_THREADS) k_raygen_mega(
-    const FrameParams fp,
-    const SceneDevice scene,
-    const std::uint32_t* __restrict__ ownedTiles,
-    PathQueue           paths,
-    std::uint32_t*      meta,
-    std::uint32_t*      ready,
-    const std::uint32_t log2Cap,
-    std::uint32_t*      pathCount,
-    float4*             radiance,
-    unsigned long long* stats)
-{
-    const std::uint32_t total = fp.numOwnedTiles * TILE_PIXELS;
-    std::uint32_t       generated = 0;
-    for (std::uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < ((total + 31u) & ~31u); slot += gridDim.x * blockDim.x)
-    {
-        std::uint32_t       px = 0, py = 0;
-        const bool          valid = slot < total && slotToPixel(fp, ownedTiles, slot, px, py);
-        const std::uint32_t dst = warpAppend(pathCount, valid);
-        if (!valid) continue;
-        ++generated;
-        std::uint32_t idx;
-        V3            origin, dir;
-        primaryRay(fp, scene, px, py, idx, origin, dir);
-        paths.originPix[dst] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(idx));
-        paths.direction[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-        paths.throughput[dst] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        meta[dst] = 1u | META_DO_CLOSEST;
-        ready[dst] = ringEntry(dst, log2Cap, dst);
-        radiance[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-    warpStatAdd(&stats[STAT_PATHS], generated);
-}
-
-__global__ void k_mega_init(MegaControl* ctl, const std::uint32_t* pathCount)
-{
-    const std::uint32_t n = *pathCount;
-    ctl->head = 0u;
-    ctl->tail = n;
-    ctl->avail = static_cast<int>(n);
-    ctl->live = n;
-}
-
-// ---- warp-specialised persistent kernel -------------------------------------------------------------
-// A block = TRAVERSAL_WARPS warps that only trace (traceRays with MegaIO) + 1 warp that only shades.  Finished
-// closest-hit rays go from the traversal lanes to the shading warp through a shared-memory ring; the shading
-// warp handles 32 paths at a time (dense) and appends the survivors to the global ready ring.  Keeping the
-// shading code out of the traversal warps' instruction stream keeps both under 64 registers without spills.
-constexpr std::uint32_t HIT_RING_CAP = 128; // entries per block; a power of two (every KB of shared memory is a KB less L1)
+// ready-ring entry (16 bit): slot | flags
+constexpr std::uint32_t LOOP_SLOT_MASK = 1023u;
+constexpr std::uint32_t READY_SHADOW = 1u << 10;  // trace the shadow ray first
+constexpr std::uint32_t READY_CLOSEST = 1u << 11; // trace the closest-hit ray (after the shadow ray, if any)
+// what a traversal lane carries for its ray (traceRays' rayIdx), and word 0 of a hit-ring entry
+constexpr std::uint32_t LANE_CLOSEST_FOLLOWS = 1u << 11;
+constexpr std::uint32_t LANE_HAD_SHADOW = 1u << 12; // the path's shadow ray was traced on this lane just before ...
+constexpr std::uint32_t LANE_SHADOW_HIT = 1u << 13; // ... and was blocked
+constexpr std::uint32_t LANE_FINAL = 1u << 14;      // no closest-hit result in this entry: the path ends with its shadow ray
 
 template<int BLOCK>
-struct MegaShared
+struct PathLoopShared
 {
     static constexpr int WARPS = BLOCK / 32;
-    uint4              hitRing[HIT_RING_CAP];   // (path id, tri, u, v) of finished closest-hit rays
-    std::uint32_t      hitSeq[HIT_RING_CAP];    // lap tag of the entry (position / CAP + 1), written after the entry
-    std::uint32_t      ringTail;                // reserved positions (traversal lanes, atomicAdd)
-    std::uint32_t      ringHead;                // consumed positions (shading warp)
-    std::uint32_t      traversalAlive;          // traversal warps still running
-    std::uint32_t      deadCount[WARPS];        // paths ended by the warp and not yet reported to ctl->live
-    std::uint32_t      starved[WARPS];          // consecutive empty-handed waits (back-off)
-    std::uint32_t      lastFailed[WARPS];       // the warp's last request got nothing: peek at the semaphore before the next one
-    unsigned long long starvedSince[WARPS];     // %globaltimer (ns) of the first of them (watchdog)
-    std::uint32_t      blockStats[6];           // closest {rays, nodes, tris}, shadow {rays, nodes, tris}
+    static constexpr std::uint32_t MAX_SLOTS = loopMaxSlots(BLOCK), READY_CAP = MAX_SLOTS, HIT_CAP = BLOCK / 2;
+    static_assert(MAX_SLOTS <= LOOP_SLOT_MASK + 1u && (HIT_CAP & (HIT_CAP - 1u)) == 0u && (READY_CAP & (READY_CAP - 1u)) == 0u, "slot bits / ring capacities");
+    uint4          hitRing[HIT_CAP];    // (lane word, tri, u, v) of finished closest-hit rays
+    std::uint32_t  hitSeq[HIT_CAP];     // lap tag of the entry (position / CAP + 1), written after the entry
+    std::uint16_t  readyRing[2][READY_CAP]; // [0]: paths that lag behind the others of the block (served first), [1]: the rest
+    std::uint16_t  freeStack[MAX_SLOTS]; // private to the shading warp
+    std::uint16_t  grant[WARPS][32];         // entries a traversal warp has just reserved (acquire -> fetch)
+    std::uint32_t  hitTail;                  // reserved positions (traversal lanes, atomicAdd)
+    std::uint32_t  hitHead;                  // consumed positions (shading warp)
+    std::uint32_t  readyHead[2];             // reserved positions (traversal warps, CAS)
+    std::uint32_t  readyTail[2];             // published positions (shading warp)
+    std::uint32_t  levelCount[LOOP_LEVELS];  // live paths by the number of their next closest-hit ray (shading warp only)
+    std::uint32_t  done;                     // 1: the block's share of the frame is complete; 2: watchdog
+    std::uint32_t  blockStats[6];            // closest {rays, nodes, tris}, shadow {rays, nodes, tris}
 };
 
-// IO of the traversal warps.  It holds no per-lane state (everything a lane needs between fetch and finish is
-// re-read from the path record), so nothing but the traversal state lives in registers across the hot loop.
+__device__ __forceinline__ float4 ldcg4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ std::uint32_t volatileLoad(const std::uint32_t* p) { return *reinterpret_cast<const volatile std::uint32_t*>(p); }
+__device__ __forceinline__ void volatileStore(std::uint32_t* p, const std::uint32_t v) { *reinterpret_cast<volatile std::uint32_t*>(p) = v; }
+
+// IO of the traversal warps.  Nothing but the lane word (traceRays' rayIdx) lives in registers across the hot loop.
 template<int BLOCK>
-struct MegaIO
+struct PathLoopIO
 {
-    using Shared = MegaShared<BLOCK>;
+    using Shared = PathLoopShared<BLOCK>;
     static constexpr bool HANDS_OVER_STRAGGLERS = false; // rays end on the lane they started on (traversal.cuh)
 #ifdef RF_TRACE_TIMELINE
     __device__ __forceinline__ unsigned long long timelineTag() const { return 0ull; }
 #endif
-    const FrameParams& fp;
-    const SceneDevice& scene;
-    const PathQueue    paths; // path state, indexed by path id
-    std::uint32_t*     meta;
-    float4*            radiance;
-    MegaControl*       ctl;
-    std::uint32_t*     ready;
-    const std::uint32_t log2Cap;
-    Shared&            sh;
+    const float4* records; // this block's path records
+    Shared&       sh;
 
     __device__ __forceinline__ int warpId() const { return threadIdx.x >> 5; }
 
-    __device__ __forceinline__ std::uint32_t tryAcquire(const std::uint32_t want, std::uint32_t& base) const
-    {
-        std::uint32_t granted = 0, b = 0;
-        // look before you leap: thousands of starving warps must not hammer the semaphore with atomics — but a warp whose
-        // last request was granted goes straight to the atomic (one L2 round trip less per refill in the steady state)
-        if (laneId() == 0u)
-        {
-            if (sh.lastFailed[warpId()] == 0u || *reinterpret_cast<volatile int*>(&ctl->avail) > 0)
-            {
-                const int old = atomicSub(&ctl->avail, static_cast<int>(want));
-                granted = old <= 0 ? 0u : min(static_cast<std::uint32_t>(old), want);
-                if (granted < want) atomicAdd(&ctl->avail, static_cast<int>(want - granted));
-                if (granted != 0u) b = atomicAdd(&ctl->head, granted);
-            }
-            sh.lastFailed[warpId()] = granted == 0u ? 1u : 0u;
-        }
-        granted = __shfl_sync(0xFFFFFFFFu, granted, 0);
-        base = __shfl_sync(0xFFFFFFFFu, b, 0);
-        return granted;
-    }
-
+    // Reserve up to `want` entries of the ready ring.  The entries are read BEFORE the head moves (a reserved position may
+    // be overwritten by the producer as soon as the head has passed it) and parked in sh.grant for fetch().
     __device__ __forceinline__ std::uint32_t acquire(const std::uint32_t want, const bool mayWait, std::uint32_t& base, bool& exhausted) const
     {
-        const int           w = warpId();
-        const std::uint32_t granted = tryAcquire(want, base);
-        if (granted == 0u && mayWait)
+        std::uint32_t granted = 0;
+        while (true)
         {
-            // nothing to trace: report the paths this warp ended, then look at the frame
-            std::uint32_t live = 0;
+            // the ring of the lagging paths first
+            std::uint32_t head = 0, n = 0, ring = 0;
             if (laneId() == 0u)
             {
-                const std::uint32_t ended = atomicExch(&sh.deadCount[w], 0u);
-                if (ended != 0u) atomicSub(&ctl->live, ended);
-                live = *reinterpret_cast<volatile std::uint32_t*>(&ctl->live);
-                if (live != 0u)
+                head = volatileLoad(&sh.readyHead[0]);
+                n = min(want, volatileLoad(&sh.readyTail[0]) - head);
+                if (n == 0u)
                 {
-                    // exponential back-off (0.25 .. 8 us) keeps the polling traffic of idle warps off the L2
-                    const std::uint32_t starved = sh.starved[w];
-                    __nanosleep(256u << min(starved, 5u));
-                    // Watchdog: a warp that has waited 2 s without the frame ending flags the frame as failed
-                    // instead of hanging the device (a lost path would be a bug; never observed).
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (starved == 0u) sh.starvedSince[w] = now;
-                    if (now - sh.starvedSince[w] > 2000000000ull)
-                    {
-                        atomicOr(&ctl->live, 0x80000000u);
-                        live = 0x80000000u;
-                    }
-                    sh.starved[w] = starved + 1u;
+                    ring = 1u;
+                    head = volatileLoad(&sh.readyHead[1]);
+                    n = min(want, volatileLoad(&sh.readyTail[1]) - head);
                 }
             }
-            live = __shfl_sync(0xFFFFFFFFu, live, 0);
-            exhausted = live == 0u || (live & 0x80000000u) != 0u;
+            head = __shfl_sync(0xFFFFFFFFu, head, 0);
+            n = __shfl_sync(0xFFFFFFFFu, n, 0);
+            ring = __shfl_sync(0xFFFFFFFFu, ring, 0);
+            if (n == 0u) break;
+            std::uint16_t entry = 0;
+            if (laneId() < n) entry = *reinterpret_cast<const volatile std::uint16_t*>(&sh.readyRing[ring][(head + laneId()) & (PathLoopShared<BLOCK>::READY_CAP - 1u)]);
+            std::uint32_t won = 0;
+            if (laneId() == 0u) won = atomicCAS(&sh.readyHead[ring], head, head + n) == head ? 1u : 0u;
+            won = __shfl_sync(0xFFFFFFFFu, won, 0);
+            if (won != 0u)
+            {
+                sh.grant[warpId()][laneId()] = entry;
+                __syncwarp();
+                granted = n;
+                break;
+            }
         }
-        else if (laneId() == 0u)
+        if (granted == 0u)
         {
-            sh.starved[w] = 0u;
+            if (volatileLoad(&sh.done) != 0u)
+                exhausted = true;
+            else if (mayWait)
+                __nanosleep(200);
         }
+        base = 0u; // work items are indices into sh.grant
         return granted;
     }
 
     __device__ __forceinline__ bool fetch(std::uint32_t& id, V3& o, V3& d, float& tmax, bool& anyHit) const
     {
-        // `id` is a ring position: wait for its producer to publish it (lap tag), then take the path id
-        const std::uint32_t     slot = id & ((1u << log2Cap) - 1u);
-        const std::uint32_t     tag = ((id >> log2Cap) + 1u) & 63u;
-        volatile std::uint32_t* entry = ready + slot;
-        std::uint32_t           e = *entry;
-        for (std::uint32_t spins = 0; (e >> RING_ID_BITS) != tag; ++spins)
-        {
-            if (spins > (1u << 22)) // watchdog, see acquire
-            {
-                atomicOr(&ctl->live, 0x80000000u);
-                return false;
-            }
-            e = *entry;
-        }
-        id = e & RING_ID_MASK;
-
-        const std::uint32_t m = __ldcg(meta + id);
+        const std::uint32_t e = sh.grant[warpId()][id];
+        const std::uint32_t slot = e & LOOP_SLOT_MASK;
+        const float4*       rec = records + slot * LOOP_RECORD_VEC;
+        anyHit = (e & READY_SHADOW) != 0u;
+        const float4 oo = ldcg4(rec + REC_ORIGIN);
+        const float4 dd = ldcg4(rec + (anyHit ? REC_SHADOW_DIR : REC_NEXT_DIR));
+        o = v3(oo.x, oo.y, oo.z), d = v3(dd.x, dd.y, dd.z);
         tmax = 10000.0f; // T_MAX, wgsl:73
-        const float4 oPix = ldcg4(paths.originPix + id);
-        o = v3(oPix.x, oPix.y, oPix.z);
-        anyHit = (m & META_DO_SHADOW) != 0u;
-        if (anyHit)
-        {
-            d = sunSampleDirection(fp, scene, __float_as_uint(oPix.w), v3(fp.sky.sun_direction));
-        }
-        else
-        {
-            const float4 dd = ldcg4(paths.direction + id);
-            d = v3(dd.x, dd.y, dd.z);
-        }
+        id = slot | ((e & READY_CLOSEST) ? LANE_CLOSEST_FOLLOWS : 0u);
         return true;
     }
 
+    __device__ __forceinline__ void pushHit(const std::uint32_t word, const HitRecord& hit) const
+    {
+        const std::uint32_t pos = atomicAdd(&sh.hitTail, 1u);
+        std::uint32_t       spins = 0;
+        while (pos - volatileLoad(&sh.hitHead) >= PathLoopShared<BLOCK>::HIT_CAP) // back-pressure (rare)
+        {
+            if (++spins > (1u << 24) || volatileLoad(&sh.done) == 2u)
+            {
+                volatileStore(&sh.done, 2u);
+                return;
+            }
+        }
+        const std::uint32_t slot = pos & (PathLoopShared<BLOCK>::HIT_CAP - 1u);
+        sh.hitRing[slot] = make_uint4(word, hit.tri, __float_as_uint(hit.u), __float_as_uint(hit.v));
+        __threadfence_block();
+        volatileStore(&sh.hitSeq[slot], pos / PathLoopShared<BLOCK>::HIT_CAP + 1u);
+    }
+
     __device__ __forceinline__ bool finish(
-        const std::uint32_t id, const bool didHit, const HitRecord& hit, const std::uint32_t visited, const std::uint32_t tested, const bool anyHit,
-        V3& o, V3& d, float& tmax, bool& anyHitNext) const
+        std::uint32_t& id, const bool didHit, const HitRecord& hit, const std::uint32_t visited, const std::uint32_t tested, const bool anyHit,
+        V3&, V3& d, float& tmax, bool& anyHitNext) const
     {
         std::uint32_t* st = sh.blockStats + (anyHit ? 3 : 0);
         atomicAdd(st + 0, 1u);
@@ -245,181 +183,306 @@ struct MegaIO
         atomicAdd(st + 2, tested);
         if (anyHit)
         {
-            // shadowRay result folded into the NEE term, rayColor:203.  Everything that is indexed by the path id is requested
-            // up front (one L2 round trip; the next direction speculatively), only the radiance word waits for the pixel index.
-            const float4        oPix = ldcg4(paths.originPix + id);
-            const float4        c = ldcg4(paths.contribution + id);
-            const std::uint32_t m = __ldcg(meta + id);
-            const float4        dd = ldcg4(paths.direction + id);
-            const std::uint32_t idx = __float_as_uint(oPix.w);
-            const float         vis = didHit ? 0.0f : 1.0f;
-            float4              rad = ldcg4(radiance + idx);
-            rad.x += c.x * vis * fp.solarInvPdf;
-            rad.y += c.y * vis * fp.solarInvPdf;
-            rad.z += c.z * vis * fp.solarInvPdf;
-            __stcg(radiance + idx, rad);
-            if (m & META_DO_CLOSEST)
+            // "Returns 1.0 if no forward intersections, 0.0 otherwise": one bit, folded into the path's radiance by the shading warp
+            id |= LANE_HAD_SHADOW | (didHit ? LANE_SHADOW_HIT : 0u);
+            if (id & LANE_CLOSEST_FOLLOWS)
             {
-                // the same lane goes on with the path's next closest-hit ray
-                o = v3(oPix.x, oPix.y, oPix.z);
+                // the same lane goes on with the path's next closest-hit ray: same origin, new direction
+                const float4 dd = ldcg4(records + (id & LOOP_SLOT_MASK) * LOOP_RECORD_VEC + REC_NEXT_DIR);
                 d = v3(dd.x, dd.y, dd.z);
                 tmax = 10000.0f;
                 anyHitNext = false;
                 return true;
             }
-            atomicAdd(&sh.deadCount[warpId()], 1u); // last bounce: the path ends with its shadow ray
+            pushHit(id | LANE_FINAL, HitRecord{RF_NO_HIT, 0.f, 0.f, 0.f}); // last bounce: the path ends with its shadow ray
             return false;
         }
-        // closest-hit ray done: hand the path to the block's shading warp
-        const std::uint32_t pos = atomicAdd(&sh.ringTail, 1u);
-        while (pos - *reinterpret_cast<volatile std::uint32_t*>(&sh.ringHead) >= HIT_RING_CAP) {} // back-pressure (rare)
-        const std::uint32_t slot = pos & (HIT_RING_CAP - 1u);
-        sh.hitRing[slot] = make_uint4(id, hit.tri, __float_as_uint(hit.u), __float_as_uint(hit.v));
-        __threadfence_block();
-        *reinterpret_cast<volatile std::uint32_t*>(&sh.hitSeq[slot]) = pos / HIT_RING_CAP + 1u;
+        pushHit(id, hit);
         return false;
     }
 };
 
-// The shading warp: rayColor:181-234 minus the traversals for 32 paths at a time, survivors appended to the
-// global ready ring (stream compaction), ended paths reported to ctl->live.
+// The shading warp: ray generation for 32 pixels at a time, rayColor:181-234 minus the traversals for 32 paths at a time,
+// path slots, the ready ring, termination.
 template<int BLOCK>
-__device__ __forceinline__ void megaShadeLoop(
-    const FrameParams&  fp,
-    const SceneDevice&  scene,
-    const PathQueue     paths,
-    std::uint32_t*      meta,
-    float4*             radiance,
-    MegaControl*        ctl,
-    std::uint32_t*      ready,
-    const std::uint32_t log2Cap,
-    MegaShared<BLOCK>&  sh)
+__device__ __forceinline__ void pathLoopShadeWarp(
+    const FrameParams&   fp,
+    const SceneDevice&   scene,
+    const std::uint32_t* __restrict__ ownedTiles,
+    float4*              records,
+    const std::uint32_t  numSlots,
+    float4*              radiance,
+    std::uint32_t*       pixelCursor,
+    unsigned long long*  stats,
+    PathLoopShared<BLOCK>& sh)
 {
-    const V3      sunDir = v3(fp.sky.sun_direction);
-    std::uint32_t head = 0, waited = 0;
+    const V3            sunDir = v3(fp.sky.sun_direction);
+    const std::uint32_t lane = laneId();
+    const std::uint32_t lanesBelow = (1u << lane) - 1u;
+    const std::uint32_t totalPixelSlots = fp.numOwnedTiles * TILE_PIXELS; // a multiple of 32
+    // The first pixels of a block are a fixed share (groups of 32, interleaved over the blocks: block b takes groups b, b + G,
+    // ...), so that a frame with few paths per block is dealt evenly; the rest is taken from the cursor as slots become free.
+    const std::uint32_t staticGroups = min((totalPixelSlots / 32u) / gridDim.x, numSlots / 32u);
+    const std::uint32_t dynamicBase = staticGroups * gridDim.x * 32u;
+    std::uint32_t       staticTaken = 0;
+    for (std::uint32_t i = lane; i < numSlots; i += 32u) sh.freeStack[i] = static_cast<std::uint16_t>(numSlots - 1u - i);
+    __syncwarp();
+    std::uint32_t freeTop = numSlots; // freeStack[0, freeTop) are free slots
+    std::uint32_t hitHead = 0, waited = 0, generated = 0;
+    std::uint32_t readyTail[2] = {0u, 0u};
+    if (lane < LOOP_LEVELS) sh.levelCount[lane] = 0u;
+    __syncwarp();
+    bool          cursorDry = false;
+    unsigned long long lastProgress = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(lastProgress));
+
+    // Scheduling priority: longest remaining path first.  Paths whose next ray is at most one bounce ahead of the block's
+    // least advanced live path go to ring 0, which the traversal warps serve first; the others wait in ring 1.  A path that
+    // was held up by a long ray (~10^3 node visits against ~90 on average) then skips the queue until it has caught up,
+    // instead of finishing alone long after the others.
+    const auto levelOf = [](const std::uint32_t bounce) { return min(bounce, LOOP_LEVELS - 1u); };
+    const auto leastAdvancedLevel = [&]() {
+        const unsigned occupied = __ballot_sync(0xFFFFFFFFu, lane < LOOP_LEVELS && sh.levelCount[lane] != 0u);
+        return occupied != 0u ? static_cast<std::uint32_t>(__ffs(occupied) - 1) : 0u;
+    };
+    // Append the paths of the lanes with `pred` to their ready rings (entries first, then the tails).
+    const auto publish = [&](const bool pred, const std::uint32_t entry, const std::uint32_t level) {
+        if (__ballot_sync(0xFFFFFFFFu, pred) == 0u) return;
+        const std::uint32_t minLevel = leastAdvancedLevel();
+        const bool          urgent = level <= minLevel + 1u;
+#pragma unroll
+        for (std::uint32_t ring = 0; ring < 2u; ++ring)
+        {
+            const bool     mine = pred && (urgent ? 0u : 1u) == ring;
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, mine);
+            if (mine) sh.readyRing[ring][(readyTail[ring] + static_cast<std::uint32_t>(__popc(mask & lanesBelow))) & (PathLoopShared<BLOCK>::READY_CAP - 1u)] = static_cast<std::uint16_t>(entry);
+            readyTail[ring] += static_cast<std::uint32_t>(__popc(mask));
+        }
+        __threadfence(); // the path records (global) and the ring entries before the tails
+        __syncwarp();
+        if (lane < 2u) volatileStore(&sh.readyTail[lane], lane == 0u ? readyTail[0] : readyTail[1]);
+    };
+
+#ifdef RF_TRACE_TIMELINE
+    const unsigned long long tlStart = globalTimerNs();
+    unsigned long long       tlBusy = 0, tlMark = 0;
+    std::uint32_t            tlBatches = 0, tlEntries = 0;
+#endif
     while (true)
     {
-        const std::uint32_t tail = *reinterpret_cast<volatile std::uint32_t*>(&sh.ringTail);
-        const std::uint32_t alive = *reinterpret_cast<volatile std::uint32_t*>(&sh.traversalAlive);
-        const std::uint32_t avail = tail - head;
-        if (avail == 0u)
+#ifdef RF_TRACE_TIMELINE
+        if (tlMark != 0) tlBusy += globalTimerNs() - tlMark; // the previous iteration generated or shaded
+        tlMark = 0;
+#endif
+        const std::uint32_t avail = volatileLoad(&sh.hitTail) - hitHead;
+        const std::uint32_t waiting = (readyTail[0] - volatileLoad(&sh.readyHead[0])) + (readyTail[1] - volatileLoad(&sh.readyHead[1]));
+        if (volatileLoad(&sh.done) == 2u) break;
+
+        // ---- new paths: 32 pixels from the frame's cursor --------------------------------------------------
+        if (!cursorDry && freeTop >= 32u && (waiting < 64u || avail < 32u))
         {
-            if (alive == 0u) break;
-            __nanosleep(500);
+#ifdef RF_TRACE_TIMELINE
+            tlMark = globalTimerNs();
+#endif
+            std::uint32_t base = 0;
+            if (staticTaken < staticGroups)
+            {
+                base = (blockIdx.x + staticTaken++ * gridDim.x) * 32u;
+            }
+            else
+            {
+                if (lane == 0u) base = dynamicBase + atomicAdd(pixelCursor, 32u);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + 32u >= totalPixelSlots) cursorDry = true;
+                if (base >= totalPixelSlots) continue;
+            }
+            std::uint32_t  px = 0, py = 0;
+            const bool     valid = slotToPixel(fp, ownedTiles, base + lane, px, py);
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, valid);
+            std::uint32_t  slot = 0;
+            if (valid)
+            {
+                slot = sh.freeStack[freeTop - 1u - static_cast<std::uint32_t>(__popc(mask & lanesBelow))];
+                std::uint32_t idx;
+                V3            origin, dir;
+                primaryRay(fp, scene, px, py, idx, origin, dir);
+                float4* rec = records + slot * LOOP_RECORD_VEC;
+                __stcg(rec + REC_ORIGIN, make_float4(origin.x, origin.y, origin.z, __uint_as_float(1u)));
+                __stcg(rec + REC_SHADOW_DIR, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(idx)));
+                __stcg(rec + REC_NEXT_DIR, make_float4(dir.x, dir.y, dir.z, 0.0f));
+                __stcg(rec + REC_THROUGHPUT, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+                __stcg(rec + REC_RADIANCE, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                ++generated;
+            }
+            freeTop -= static_cast<std::uint32_t>(__popc(mask));
+            if (lane == 0u) sh.levelCount[1] += static_cast<std::uint32_t>(__popc(mask));
+            __syncwarp();
+            publish(valid, slot | READY_CLOSEST, 1u);
             continue;
         }
-        if (avail < 32u && alive != 0u && waited < scene.tuning.shadeWait)
+
+        if (avail == 0u)
         {
-            // let the batch fill for up to ~8 us: a dense batch costs the same as a sparse one
+            if (cursorDry && freeTop == numSlots)
+            {
+                if (lane == 0u) volatileStore(&sh.done, 1u);
+                break;
+            }
+            // Watchdog: two seconds without a finished ray flag the frame as failed instead of hanging the device (a lost
+            // path would be a bug; never observed).
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - lastProgress > 2000000000ull)
+            {
+                if (lane == 0u) volatileStore(&sh.done, 2u);
+                break;
+            }
+            __nanosleep(200);
+            continue;
+        }
+        if (avail < 32u && waiting >= 32u && waited < scene.tuning.shadeWait)
+        {
+            // the lanes have rays to go on with: let the batch fill (a dense batch costs the same as a sparse one)
             ++waited;
             __nanosleep(500);
             continue;
         }
         waited = 0u;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(lastProgress));
+
+        // ---- shade up to 32 finished closest-hit rays ---------------------------------------------------
         const std::uint32_t n = min(avail, 32u);
-        const bool          mine = laneId() < n;
+#ifdef RF_TRACE_TIMELINE
+        tlMark = globalTimerNs();
+        ++tlBatches, tlEntries += n;
+#endif
         bool                survives = false, ended = false;
-        std::uint32_t       id = 0;
-        if (mine)
+        std::uint32_t       slot = 0, entry = 0, level = 0;
+        if (lane < n)
         {
-            const std::uint32_t pos = head + laneId();
-            const std::uint32_t slot = pos & (HIT_RING_CAP - 1u);
-            while (*reinterpret_cast<volatile std::uint32_t*>(&sh.hitSeq[slot]) != pos / HIT_RING_CAP + 1u) {} // entry being written
-            __threadfence_block();
-            const uint4 e = sh.hitRing[slot];
-            id = e.x;
-            const HitRecord     hit{e.y, __uint_as_float(e.z), __uint_as_float(e.w), 0.0f};
-            const std::uint32_t m = __ldcg(meta + id);
-            const std::uint32_t bounce = m & META_BOUNCE_MASK;
-            const float4        oPix = ldcg4(paths.originPix + id);
-            const float4        thr = ldcg4(paths.throughput + id);
-            const std::uint32_t idx = __float_as_uint(oPix.w);
-            if (hit.tri == RF_NO_HIT)
+            const std::uint32_t pos = hitHead + lane;
+            const std::uint32_t ringSlot = pos & (PathLoopShared<BLOCK>::HIT_CAP - 1u);
+            std::uint32_t       spins = 0;
+            while (volatileLoad(&sh.hitSeq[ringSlot]) != pos / PathLoopShared<BLOCK>::HIT_CAP + 1u) // entry being written
             {
-                const float4 dir = ldcg4(paths.direction + id);
-                const V3     sky = skyForMiss(fp, v3(dir.x, dir.y, dir.z), sunDir);
-                float4       rad = ldcg4(radiance + idx);
+                if (++spins > (1u << 24))
+                {
+                    volatileStore(&sh.done, 2u);
+                    break;
+                }
+            }
+            __threadfence_block();
+            const uint4         e = sh.hitRing[ringSlot];
+            const std::uint32_t word = e.x;
+            slot = word & LOOP_SLOT_MASK;
+            const HitRecord hit{e.y, __uint_as_float(e.z), __uint_as_float(e.w), 0.0f};
+            float4*         rec = records + slot * LOOP_RECORD_VEC;
+            // everything indexed by the slot is requested together: one L2 round trip
+            const float4        originRay = ldcg4(rec + REC_ORIGIN);
+            const std::uint32_t idx = __float_as_uint(ldcg4(rec + REC_SHADOW_DIR).w);
+            const float4        thr = ldcg4(rec + REC_THROUGHPUT);
+            const float4        c = ldcg4(rec + REC_CONTRIBUTION);
+            float4              rad = ldcg4(rec + REC_RADIANCE);
+            const float4        dir = ldcg4(rec + REC_NEXT_DIR);
+            const std::uint32_t bounce = __float_as_uint(originRay.w);
+            level = levelOf(bounce);
+            atomicSub(&sh.levelCount[level], 1u);
+            if (word & LANE_HAD_SHADOW)
+            {
+                // shadowRay result folded into the NEE term of the previous hit, rayColor:203
+                const float vis = (word & LANE_SHADOW_HIT) ? 0.0f : 1.0f;
+                rad.x += c.x * vis * fp.solarInvPdf;
+                rad.y += c.y * vis * fp.solarInvPdf;
+                rad.z += c.z * vis * fp.solarInvPdf;
+            }
+            if (word & LANE_FINAL)
+            {
+                ended = true;
+            }
+            else if (hit.tri == RF_NO_HIT)
+            {
+                const V3 sky = skyForMiss(fp, v3(dir.x, dir.y, dir.z), sunDir);
                 rad.x += thr.x * sky.x, rad.y += thr.y * sky.y, rad.z += thr.z * sky.z;
-                __stcg(radiance + idx, rad);
                 ended = true;
             }
             else
             {
                 const SurfaceShade s = shadeSurfaceHit(fp, scene, hit, idx, v3(thr.x, thr.y, thr.z), sunDir);
-                __stcg(paths.originPix + id, make_float4(s.p.x, s.p.y, s.p.z, oPix.w));
-                __stcg(paths.direction + id, make_float4(s.wi.x, s.wi.y, s.wi.z, 0.0f));
-                __stcg(paths.throughput + id, make_float4(s.nextThroughput.x, s.nextThroughput.y, s.nextThroughput.z, 0.0f));
-                __stcg(paths.contribution + id, make_float4(s.contribution.x, s.contribution.y, s.contribution.z, 0.0f));
+                __stcg(rec + REC_ORIGIN, make_float4(s.p.x, s.p.y, s.p.z, __uint_as_float(bounce + 1u)));
+                __stcg(rec + REC_SHADOW_DIR, make_float4(s.lightDir.x, s.lightDir.y, s.lightDir.z, __uint_as_float(idx)));
+                __stcg(rec + REC_NEXT_DIR, make_float4(s.wi.x, s.wi.y, s.wi.z, 0.0f));
+                __stcg(rec + REC_THROUGHPUT, make_float4(s.nextThroughput.x, s.nextThroughput.y, s.nextThroughput.z, 0.0f));
+                __stcg(rec + REC_CONTRIBUTION, make_float4(s.contribution.x, s.contribution.y, s.contribution.z, 0.0f));
+                __stcg(rec + REC_RADIANCE, rad);
                 // every hit casts a shadow ray; the path goes on unless this was the last bounce (rayColor:205-207)
-                __stcg(meta + id, (bounce + 1u) | META_DO_SHADOW | (bounce < fp.numBounces ? META_DO_CLOSEST : 0u));
+                entry = slot | READY_SHADOW | (bounce < fp.numBounces ? READY_CLOSEST : 0u);
                 survives = true;
+                level = levelOf(bounce + 1u);
+                atomicAdd(&sh.levelCount[level], 1u);
             }
+            if (ended) radiance[idx] = rad;
         }
         __syncwarp();
-        head += n;
-        if (laneId() == 0u) *reinterpret_cast<volatile std::uint32_t*>(&sh.ringHead) = head; // slots may be reused
+        hitHead += n;
+        if (lane == 0u) volatileStore(&sh.hitHead, hitHead); // ring slots may be reused
         const unsigned endedMask = __ballot_sync(0xFFFFFFFFu, ended);
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, survives);
-        if (mask != 0u)
-        {
-            const std::uint32_t count = static_cast<std::uint32_t>(__popc(mask));
-            std::uint32_t       pos = 0;
-            if (laneId() == 0u) pos = atomicAdd(&ctl->tail, count);
-            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-            __threadfence(); // path state before its ring entry
-            if (survives)
-            {
-                const std::uint32_t at = pos + static_cast<std::uint32_t>(__popc(mask & ((1u << laneId()) - 1u)));
-                *reinterpret_cast<volatile std::uint32_t*>(ready + (at & ((1u << log2Cap) - 1u))) = ringEntry(at, log2Cap, id);
-            }
-            __threadfence();
-            __syncwarp();
-            if (laneId() == 0u) atomicAdd(&ctl->avail, static_cast<int>(count));
-        }
-        if (laneId() == 0u && endedMask != 0u) atomicSub(&ctl->live, static_cast<std::uint32_t>(__popc(endedMask)));
+        if (ended) sh.freeStack[freeTop + static_cast<std::uint32_t>(__popc(endedMask & lanesBelow))] = static_cast<std::uint16_t>(slot);
+        freeTop += static_cast<std::uint32_t>(__popc(endedMask));
+        __syncwarp();
+        publish(survives, entry, level);
     }
+#ifdef RF_TRACE_TIMELINE
+    generated = __reduce_add_sync(0xFFFFFFFFu, generated);
+    if (lane == 0u && g_timeline != nullptr)
+    {
+        // one record per shading warp: tag 2, dry = ns spent generating / shading, rays = hit entries, rounds = batches, pad = paths
+        const std::uint32_t at = atomicAdd(&g_timelineCount, 1u);
+        if (at < g_timelineCap) g_timeline[at] = TimelineRecord{2ull, tlStart, tlBusy, globalTimerNs(), tlEntries, tlBatches, 0u, generated};
+    }
+    if (lane != 0u) generated = 0u;
+#endif
+    warpStatAdd(&stats[STAT_PATHS], generated);
 }
 
-template<int VARIANT, int BLOCK>
+template<int BLOCK, int STACK>
+constexpr std::size_t megaSharedBytes() { return static_cast<std::size_t>(STACK) * BLOCK * 4u; }
+
+template<int VARIANT, int BLOCK, int STACK = RF_STACK_SIZE>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_mega(
     const __grid_constant__ FrameParams fp,
     const __grid_constant__ SceneDevice scene,
-    const PathQueue     paths,
-    std::uint32_t*      meta,
+    const std::uint32_t* __restrict__ ownedTiles,
+    float4*             records,      // gridDim.x x slotsPerBlock x LOOP_RECORD_VEC
+    const std::uint32_t slotsPerBlock,
     float4*             radiance,
-    MegaControl*        ctl,
-    std::uint32_t*      ready,
-    const std::uint32_t log2Cap,
+    std::uint32_t*      pixelCursor,
+    std::uint32_t*      failed,       // set to 1 when a block left on its watchdog
     unsigned long long* stats)
 {
-    using Shared = MegaShared<BLOCK>;
+    using Shared = PathLoopShared<BLOCK>;
     constexpr int TRAVERSAL_WARPS = Shared::WARPS - 1;
     static_assert(TRAVERSAL_WARPS >= 1, "need at least one traversal warp and one shading warp");
-    __shared__ Shared sh;
+    // the block's control structures are static shared memory; the traversal stacks (up to 64 KB for 512 threads, more than a
+    // static allocation may have) are the kernel's dynamic shared memory (megaSharedBytes)
+    __shared__ Shared       sh;
+    extern __shared__ uint4 megaStackMemory[];
+    std::uint32_t* const    stackMemory = reinterpret_cast<std::uint32_t*>(megaStackMemory);
     if (threadIdx.x < 6) sh.blockStats[threadIdx.x] = 0u;
-    if (threadIdx.x < Shared::WARPS) sh.deadCount[threadIdx.x] = 0u, sh.starved[threadIdx.x] = 0u, sh.lastFailed[threadIdx.x] = 0u;
-    for (std::uint32_t i = threadIdx.x; i < HIT_RING_CAP; i += BLOCK) sh.hitSeq[i] = 0u;
-    if (threadIdx.x == 0) sh.ringTail = 0u, sh.ringHead = 0u, sh.traversalAlive = TRAVERSAL_WARPS;
+    for (std::uint32_t i = threadIdx.x; i < Shared::HIT_CAP; i += BLOCK) sh.hitSeq[i] = 0u;
+    if (threadIdx.x == 0) sh.hitTail = 0u, sh.hitHead = 0u, sh.readyHead[0] = sh.readyHead[1] = 0u, sh.readyTail[0] = sh.readyTail[1] = 0u, sh.done = 0u;
     __syncthreads();
+    float4* const blockRecords = records + static_cast<std::uint64_t>(blockIdx.x) * slotsPerBlock * LOOP_RECORD_VEC;
     if (static_cast<int>(threadIdx.x >> 5) < TRAVERSAL_WARPS)
     {
-        MegaIO<BLOCK> io{fp, scene, paths, meta, radiance, ctl, ready, log2Cap, sh};
-        traceRays<2, VARIANT, BLOCK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
-        // paths ended by this warp that it has not reported yet (it may have left on the watchdog)
-        __syncwarp();
-        if (laneId() == 0u)
-        {
-            const std::uint32_t ended = atomicExch(&sh.deadCount[threadIdx.x >> 5], 0u);
-            if (ended != 0u) atomicSub(&ctl->live, ended);
-            __threadfence_block();
-            atomicSub(&sh.traversalAlive, 1u);
-        }
+        PathLoopIO<BLOCK> io{blockRecords, sh};
+        traceRays<2, VARIANT, BLOCK, PathLoopIO<BLOCK>, STACK, true>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io, stackMemory);
     }
     else
     {
-        megaShadeLoop<BLOCK>(fp, scene, paths, meta, radiance, ctl, ready, log2Cap, sh);
+        pathLoopShadeWarp<BLOCK>(fp, scene, ownedTiles, blockRecords, slotsPerBlock, radiance, pixelCursor, stats, sh);
     }
     __syncthreads();
+    if (threadIdx.x == 0 && sh.done == 2u) atomicExch(failed, 1u);
     if (threadIdx.x < 6 && sh.blockStats[threadIdx.x] != 0u)
     {
         const int slot[6] = {STAT_CLOSEST_RAYS, STAT_CLOSEST_NODES, STAT_CLOSEST_TRIS, STAT_SHADOW_RAYS, STAT_SHADOW_NODES, STAT_SHADOW_TRIS};

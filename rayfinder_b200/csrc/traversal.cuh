@@ -253,6 +253,10 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Lane occupancy over time: per 16.4 us bucket of %globaltimer (absolute, 256 buckets = 4.2 ms), the number of loop rounds
+// the traversal warps went through and the lanes that held a ray in them (tools/occupancy_timeline.py).
+constexpr int      OCC_BUCKETS = 256;
+__device__ unsigned long long g_occBusy[OCC_BUCKETS], g_occRounds[OCC_BUCKETS];
 #endif
 
 // The persistent traversal loop.  IO supplies the rays and consumes the results:
@@ -277,20 +281,24 @@ constexpr int TRACE_DEFAULT_VARIANT = 3;
 // interior node needs fewer (validateBvh) can run with a smaller shared-memory stack, which decides the SM's
 // shared-memory carve-out and therefore how much L1 is left for the nodes: 4 blocks x (32 x 256 x 4 B + 1 KB) need the
 // 164 KB carve-out (88 KB of L1), 31 entries fit the 132 KB one (120 KB of L1), 23 entries the 100 KB one.
-template<int MODE, int VARIANT, int BLOCK, class IO, int STACK = 32>
+// EXTERNAL_STACK: the caller supplies the STACK * BLOCK words of stack memory (a kernel whose shared memory exceeds the 48 KB
+// a static allocation may have passes a piece of its dynamic shared memory); otherwise the function declares them itself.
+template<int MODE, int VARIANT, int BLOCK, class IO, int STACK = 32, bool EXTERNAL_STACK = false>
 __device__ __forceinline__ void traceRays(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
     const bool          sceneOrdered,
     const TraceTuning   tuning,
-    IO&                 io)
+    IO&                 io,
+    std::uint32_t*      externalStack = nullptr)
 {
-    // Traversal stack: column `threadIdx.x` of a [32][blockDim.x] shared array (entry k of this thread
-    // lives STACK_STRIDE * k bytes above stackBase; bank = lane for every k).
+    // Traversal stack: a [warp][entry][lane] shared array — entry k of this thread lives STACK_STRIDE * k bytes above
+    // stackBase, bank = lane for every k, and the STACK x 128 bytes of a warp are contiguous.
     static_assert(STACK >= 1 && STACK <= RF_STACK_SIZE, "the reference's stack has 32 entries");
-    __shared__ std::uint32_t stackMem[STACK * BLOCK];
-    constexpr std::uint32_t  STACK_STRIDE = BLOCK * 4u;
-    const std::uint32_t      stackBase = static_cast<std::uint32_t>(__cvta_generic_to_shared(stackMem + threadIdx.x));
+    __shared__ std::uint32_t ownStack[EXTERNAL_STACK ? 1 : STACK * BLOCK];
+    std::uint32_t* const     stackMem = EXTERNAL_STACK ? externalStack : ownStack;
+    constexpr std::uint32_t  STACK_STRIDE = 32u * 4u;
+    const std::uint32_t      stackBase = static_cast<std::uint32_t>(__cvta_generic_to_shared(stackMem + (threadIdx.x >> 5) * (STACK * 32) + (threadIdx.x & 31u)));
     std::uint32_t            stackTop = stackBase; // address of the next free entry
 
     enum : int
@@ -470,6 +478,7 @@ __device__ __forceinline__ void traceRays(
     const unsigned long long tlStart = globalTimerNs();
     unsigned long long       tlDry = 0;
     std::uint32_t            tlRays = 0, tlRounds = 0, tlMaxNodes = 0;
+    std::uint32_t            tlOccBucket = 0xFFFFFFFFu, tlOccBusy = 0, tlOccRounds = 0;
 #endif
 
     while (true)
@@ -477,6 +486,21 @@ __device__ __forceinline__ void traceRays(
 #ifdef RF_TRACE_TIMELINE
         ++tlRounds;
         if (exhausted && tlDry == 0) tlDry = globalTimerNs();
+        tlOccBusy += static_cast<std::uint32_t>(__popc(__ballot_sync(0xFFFFFFFFu, state != IDLE)));
+        ++tlOccRounds;
+        if ((tlRounds & 3u) == 0u)
+        {
+            const std::uint32_t bucket = static_cast<std::uint32_t>(globalTimerNs() >> 14) & (OCC_BUCKETS - 1);
+            if (bucket != tlOccBucket)
+            {
+                if (laneId() == 0u && tlOccBucket != 0xFFFFFFFFu)
+                {
+                    atomicAdd(&g_occBusy[tlOccBucket], static_cast<unsigned long long>(tlOccBusy));
+                    atomicAdd(&g_occRounds[tlOccBucket], static_cast<unsigned long long>(tlOccRounds));
+                }
+                tlOccBucket = bucket, tlOccBusy = 0u, tlOccRounds = 0u;
+            }
+        }
 #endif
         // ---- node steps: one BVH node per lane in NODE state ------------------------------------------
 #pragma unroll
@@ -585,6 +609,11 @@ __device__ __forceinline__ void traceRays(
         }
     }
 #ifdef RF_TRACE_TIMELINE
+    if (laneId() == 0u && tlOccBucket != 0xFFFFFFFFu)
+    {
+        atomicAdd(&g_occBusy[tlOccBucket], static_cast<unsigned long long>(tlOccBusy));
+        atomicAdd(&g_occRounds[tlOccBucket], static_cast<unsigned long long>(tlOccRounds));
+    }
     tlMaxNodes = __reduce_max_sync(0xFFFFFFFFu, tlMaxNodes & 0xFFFFu) | (__reduce_max_sync(0xFFFFFFFFu, tlMaxNodes >> 16) << 16);
     if (laneId() == 0u && g_timeline != nullptr)
     {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A/B of the traversal kernels and their scheduling knobs on one GPU (Sponza, 8 bounces): ms per frame and Mrays/s.
 
-    python tools/kernel_ab.py [WxH ...] [--configs "kernel:pair_variant:sub_frames:blocks:tri_min:refill_min,..."] [--frames N]
+    python tools/kernel_ab.py [WxH ...] [--configs "kernel:pair_variant:sub_frames:blocks:tri_min:refill_min[:evict_max[:persistent]],..."] [--frames N]
 
 kernel 1 = one node per visit (traversal.cuh), 2 = child-pair records (traversal_pairs.cuh); sub_frames -1 = automatic.
 """
@@ -35,12 +35,13 @@ def main():
             fields = [int(x) for x in cfg.split(":")]
             kernel, variant, sub_frames, blocks, tri_min, refill_min = fields[:6]
             evict = fields[6] if len(fields) > 6 else -1
+            persistent = fields[7] if len(fields) > 7 else 0
             ren.set_option("trace_kernel", kernel)
             if kernel == 2:
                 ren.set_option("pair_variant", variant)
-                ren.set_pipeline(sub_frames, 0, -1, 0)
+                ren.set_pipeline(sub_frames, persistent, -1, 0)
             else:
-                ren.set_pipeline(sub_frames, 0, variant, 256)
+                ren.set_pipeline(sub_frames, persistent, variant, 256)
             for item in filter(None, args.options.split(",")):
                 name, value = item.split("=")
                 ren.set_option(name, int(value))
@@ -54,7 +55,7 @@ def main():
                 ren.render()
             s = ren.stats()
             rays = s["closest_rays"] + s["shadow_rays"]
-            print(f"{w}x{h} kernel={kernel} variant={variant} sub_frames={s['sub_frames']} evict={s['evict_max']} blocks={blocks} tri_min={tri_min} "
+            print(f"{w}x{h} persistent={persistent} kernel={kernel} variant={variant} sub_frames={s['sub_frames']} evict={s['evict_max']} blocks={blocks} tri_min={tri_min} "
                   f"refill_min={refill_min}: {s['device_ms_total'] / args.frames:7.3f} ms/frame  {rays / s['device_ms_total'] / 1e3:8.1f} Mrays/s  "
                   f"records/ray {s['node_records_loaded'] / rays:6.2f}  visits/ray {(s['closest_nodes_visited'] + s['shadow_nodes_visited']) / rays:6.2f}", flush=True)
         ren.close()
