@@ -71,6 +71,7 @@ struct PathLoopShared
     std::uint32_t  readyHead[2];             // reserved positions (traversal warps, CAS)
     std::uint32_t  readyTail[2];             // published positions (shading warp)
     std::uint32_t  levelCount[LOOP_LEVELS];  // live paths by the number of their next closest-hit ray (shading warp only)
+    std::uint32_t  tail;                     // 1: few paths are left (PathLoopIO::tailPhase)
     std::uint32_t  done;                     // 1: the block's share of the frame is complete; 2: watchdog
     std::uint32_t  blockStats[6];            // closest {rays, nodes, tris}, shadow {rays, nodes, tris}
 };
@@ -84,21 +85,30 @@ template<int BLOCK>
 struct PathLoopIO
 {
     using Shared = PathLoopShared<BLOCK>;
-    static constexpr bool HANDS_OVER_STRAGGLERS = false; // rays end on the lane they started on (traversal.cuh)
+    static constexpr bool HANDS_OVER_STRAGGLERS = false;   // no ray leaves its warp ...
+    static constexpr bool WALKS_LAST_RAY_WITH_WARP = true; // ... but at the end of the frame a warp walks its last ray with all lanes
 #ifdef RF_TRACE_TIMELINE
     __device__ __forceinline__ unsigned long long timelineTag() const { return 0ull; }
 #endif
     const float4* records; // this block's path records
     Shared&       sh;
 
+    // The block's share of the frame is nearly done (set by the shading warp): warps take one ray at a time and walk it
+    // with all 32 lanes.
+    // (Warp-collective: the flag changes under the warp's feet, and lanes that read it at different moments must not take
+    // different sides of a branch that contains warp-synchronous code.)
+    __device__ __forceinline__ bool tailPhase() const { return __any_sync(0xFFFFFFFFu, volatileLoad(&sh.tail) != 0u) != 0; }
+
     __device__ __forceinline__ int warpId() const { return threadIdx.x >> 5; }
 
     // Reserve up to `want` entries of the ready ring.  The entries are read BEFORE the head moves (a reserved position may
     // be overwritten by the producer as soon as the head has passed it) and parked in sh.grant for fetch().
-    __device__ __forceinline__ std::uint32_t acquire(const std::uint32_t want, const bool mayWait, std::uint32_t& base, bool& exhausted) const
+    __device__ __forceinline__ std::uint32_t acquire(std::uint32_t want, const bool mayWait, std::uint32_t& base, bool& exhausted) const
     {
+        // at the end of the frame: one ray per warp, and only for a warp that holds none
+        if (tailPhase()) want = mayWait ? 1u : 0u;
         std::uint32_t granted = 0;
-        while (true)
+        while (want != 0u)
         {
             // the ring of the lagging paths first
             std::uint32_t head = 0, n = 0, ring = 0;
@@ -132,7 +142,7 @@ struct PathLoopIO
         }
         if (granted == 0u)
         {
-            if (volatileLoad(&sh.done) != 0u)
+            if (__any_sync(0xFFFFFFFFu, volatileLoad(&sh.done) != 0u)) // (warp-collective, see tailPhase)
                 exhausted = true;
             else if (mayWait)
                 __nanosleep(200);
@@ -202,6 +212,116 @@ struct PathLoopIO
     }
 };
 
+// A whole ray with the literal (NaN-propagating) slab test on ONE lane, its stack in `stack` (32 words of shared memory): the
+// tail loop's rare path for rays the fast slab form cannot take (traceRays' traceExactRay).
+template<class IO>
+__device__ __forceinline__ void traceLiteralRay(const PackedNode* nodes, const float4* tris, WarpRay* ray, std::uint32_t* stack, IO* io)
+{
+    WarpRay&            r = *ray;
+    const float         ix = __fdiv_rn(1.0f, r.d.x), iy = __fdiv_rn(1.0f, r.d.y), iz = __fdiv_rn(1.0f, r.d.z);
+    const std::uint32_t negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
+    std::uint32_t       cur = 0, sp = 0, visited = 0, tested = 0;
+    float               tmax = r.tmax;
+    HitRecord           hit{RF_NO_HIT, 0.f, 0.f, 0.f};
+    while (true)
+    {
+        ++visited;
+        const PackedNode    nd = loadNode(nodes + cur);
+        const bool          boxHit = slabTestExact(nd, negMask, r.o, ix, iy, iz, tmax);
+        const std::uint32_t kind = nd.b & 3u;
+        if (boxHit && kind != 3u)
+        {
+            const bool neg = (negMask >> kind) & 1u;
+            stack[sp++] = neg ? cur + 1u : nd.a;
+            cur = neg ? nd.a : cur + 1u;
+            continue;
+        }
+        bool done = false;
+        if (boxHit)
+        {
+            const std::uint32_t end = nd.a + (nd.b >> 2);
+            for (std::uint32_t tri = nd.a; tri != end && !done; ++tri)
+            {
+                ++tested;
+                float u, v, t;
+                if (intersectTriangle(tris, tri, r.o, r.d, tmax, u, v, t))
+                {
+                    hit.tri = tri, hit.u = u, hit.v = v, hit.t = t;
+                    if (r.anyHit)
+                        done = true;
+                    else
+                        tmax = t;
+                }
+            }
+        }
+        if (done || sp == 0u) break;
+        cur = stack[--sp];
+    }
+    bool anyHitNext = false;
+    r.state = io->finish(r.rayIdx, hit.tri != RF_NO_HIT, hit, visited, tested, r.anyHit, r.o, r.d, r.tmax, anyHitNext) ? 1 : 0;
+    r.anyHit = anyHitNext;
+}
+
+// The end of a block's share of the frame (PathLoopIO::tailPhase): the warp takes one ray at a time from the ready rings and
+// walks it — and the rays chained to it — with all 32 lanes (traceWarpRay, straggler.cuh), using its own traversal-stack
+// memory (>= 1152 bytes) as the walk's scratch.  `r` = the ray the warp held when it left traceRays (state 0: none).
+template<int BLOCK>
+__device__ __forceinline__ void pathLoopTail(const PackedNode* __restrict__ nodes, const float4* __restrict__ tris, PathLoopIO<BLOCK>& io, WarpRay& r, std::uint32_t* scratch)
+{
+    StragglerWindowShared& win = *reinterpret_cast<StragglerWindowShared*>(scratch);
+    const std::uint32_t    lane = laneId();
+    std::uint32_t          parity = 0;
+    bool                   have = r.state != 0, exhausted = false;
+    while (true)
+    {
+        if (!have)
+        {
+            std::uint32_t base = 0;
+            if (io.acquire(1u, true, base, exhausted) == 0u)
+            {
+                if (exhausted) break;
+                continue;
+            }
+            std::uint32_t id = 0;
+            V3            o = v3(0.f, 0.f, 0.f), d = o;
+            float         tmax = 0.f;
+            bool          anyHit = false;
+            if (lane == 0u) io.fetch(id, o, d, tmax, anyHit);
+            r.rayIdx = __shfl_sync(0xFFFFFFFFu, id, 0);
+            r.o = v3(__shfl_sync(0xFFFFFFFFu, o.x, 0), __shfl_sync(0xFFFFFFFFu, o.y, 0), __shfl_sync(0xFFFFFFFFu, o.z, 0));
+            r.d = v3(__shfl_sync(0xFFFFFFFFu, d.x, 0), __shfl_sync(0xFFFFFFFFu, d.y, 0), __shfl_sync(0xFFFFFFFFu, d.z, 0));
+            r.tmax = __shfl_sync(0xFFFFFFFFu, tmax, 0);
+            r.anyHit = __shfl_sync(0xFFFFFFFFu, anyHit ? 1 : 0, 0) != 0;
+            r.cur = 0u, r.pendTri = 0u, r.pendEnd = 0u, r.rayNodes = 0u, r.rayTris = 0u, r.sp = 0u;
+            r.state = 1;
+            r.hit = HitRecord{RF_NO_HIT, 0.f, 0.f, 0.f};
+        }
+        if (r.state == 1 && r.sp == 0u && r.cur == 0u)
+        {
+            // a fresh ray: one with a NaN / zero inverse direction component or a non-finite origin takes the literal slab test
+            const float ix = __fdiv_rn(1.0f, r.d.x), iy = __fdiv_rn(1.0f, r.d.y), iz = __fdiv_rn(1.0f, r.d.z);
+            if (!(ix == ix && iy == iy && iz == iz && ix != 0.0f && iy != 0.0f && iz != 0.0f && isFiniteBits(r.o.x) && isFiniteBits(r.o.y) && isFiniteBits(r.o.z)))
+            {
+                if (lane == 0u) traceLiteralRay(nodes, tris, &r, win.stack, &io);
+                __syncwarp();
+                have = __shfl_sync(0xFFFFFFFFu, r.state, 0) != 0;
+                if (have)
+                {
+                    r.rayIdx = __shfl_sync(0xFFFFFFFFu, r.rayIdx, 0);
+                    r.d = v3(__shfl_sync(0xFFFFFFFFu, r.d.x, 0), __shfl_sync(0xFFFFFFFFu, r.d.y, 0), __shfl_sync(0xFFFFFFFFu, r.d.z, 0));
+                    r.tmax = __shfl_sync(0xFFFFFFFFu, r.tmax, 0);
+                    r.anyHit = __shfl_sync(0xFFFFFFFFu, r.anyHit ? 1 : 0, 0) != 0;
+                    r.cur = 0u, r.pendTri = 0u, r.pendEnd = 0u, r.rayNodes = 0u, r.rayTris = 0u, r.sp = 0u;
+                    r.state = 1;
+                    r.hit = HitRecord{RF_NO_HIT, 0.f, 0.f, 0.f};
+                }
+                continue;
+            }
+        }
+        have = traceWarpRay<STRAGGLER_DIRECT>(nodes, tris, r, win, parity, io);
+    }
+}
+
 // The shading warp: ray generation for 32 pixels at a time, rayColor:181-234 minus the traversals for 32 paths at a time,
 // path slots, the ready ring, termination.
 template<int BLOCK>
@@ -232,7 +352,9 @@ __device__ __forceinline__ void pathLoopShadeWarp(
     std::uint32_t readyTail[2] = {0u, 0u};
     if (lane < LOOP_LEVELS) sh.levelCount[lane] = 0u;
     __syncwarp();
-    bool          cursorDry = false;
+    bool          cursorDry = false, tailFlagged = false;
+    // (tuning.tailPaths: 0 = automatic — two rays per traversal warp —, n + 1 = a threshold of n live paths, so 1 = never)
+    const std::uint32_t tailThreshold = scene.tuning.tailPaths == 0u ? 2u * (BLOCK / 32 - 1) : scene.tuning.tailPaths - 1u;
     unsigned long long lastProgress = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(lastProgress));
 
@@ -274,9 +396,22 @@ __device__ __forceinline__ void pathLoopShadeWarp(
         if (tlMark != 0) tlBusy += globalTimerNs() - tlMark; // the previous iteration generated or shaded
         tlMark = 0;
 #endif
-        const std::uint32_t avail = volatileLoad(&sh.hitTail) - hitHead;
-        const std::uint32_t waiting = (readyTail[0] - volatileLoad(&sh.readyHead[0])) + (readyTail[1] - volatileLoad(&sh.readyHead[1]));
-        if (volatileLoad(&sh.done) == 2u) break;
+        // (what the other warps change is read by one lane: every lane must take the same side of the branches below)
+        std::uint32_t avail = 0, waiting = 0, failed = 0;
+        if (lane == 0u)
+        {
+            avail = volatileLoad(&sh.hitTail) - hitHead;
+            waiting = (readyTail[0] - volatileLoad(&sh.readyHead[0])) + (readyTail[1] - volatileLoad(&sh.readyHead[1]));
+            failed = volatileLoad(&sh.done) == 2u ? 1u : 0u;
+        }
+        avail = __shfl_sync(0xFFFFFFFFu, avail, 0);
+        waiting = __shfl_sync(0xFFFFFFFFu, waiting, 0);
+        if (__shfl_sync(0xFFFFFFFFu, failed, 0) != 0u) break;
+        if (cursorDry && !tailFlagged && numSlots - freeTop <= tailThreshold)
+        {
+            tailFlagged = true;
+            if (lane == 0u) volatileStore(&sh.tail, 1u);
+        }
 
         // ---- new paths: 32 pixels from the frame's cursor --------------------------------------------------
         if (!cursorDry && freeTop >= 32u && (waiting < 64u || avail < 32u))
@@ -469,13 +604,16 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_mega(
     std::uint32_t* const    stackMemory = reinterpret_cast<std::uint32_t*>(megaStackMemory);
     if (threadIdx.x < 6) sh.blockStats[threadIdx.x] = 0u;
     for (std::uint32_t i = threadIdx.x; i < Shared::HIT_CAP; i += BLOCK) sh.hitSeq[i] = 0u;
-    if (threadIdx.x == 0) sh.hitTail = 0u, sh.hitHead = 0u, sh.readyHead[0] = sh.readyHead[1] = 0u, sh.readyTail[0] = sh.readyTail[1] = 0u, sh.done = 0u;
+    if (threadIdx.x == 0) sh.hitTail = 0u, sh.hitHead = 0u, sh.readyHead[0] = sh.readyHead[1] = 0u, sh.readyTail[0] = sh.readyTail[1] = 0u, sh.done = 0u, sh.tail = 0u;
     __syncthreads();
     float4* const blockRecords = records + static_cast<std::uint64_t>(blockIdx.x) * slotsPerBlock * LOOP_RECORD_VEC;
     if (static_cast<int>(threadIdx.x >> 5) < TRAVERSAL_WARPS)
     {
         PathLoopIO<BLOCK> io{blockRecords, sh};
-        traceRays<2, VARIANT, BLOCK, PathLoopIO<BLOCK>, STACK, true>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io, stackMemory);
+        static_assert(STACK * 128 >= static_cast<int>(sizeof(StragglerWindowShared)) && offsetof(StragglerWindowShared, stack) == 8 * 128, "the tail walk's scratch is the warp's own stack memory");
+        WarpRay leftover;
+        traceRays<2, VARIANT, BLOCK, PathLoopIO<BLOCK>, STACK, true>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io, stackMemory, &leftover);
+        pathLoopTail<BLOCK>(scene.nodes, scene.tris, io, leftover, stackMemory + (threadIdx.x >> 5) * (STACK * 32));
     }
     else
     {

@@ -28,11 +28,15 @@ constexpr int STRAGGLER_WARPS_PER_BLOCK = 4;
 constexpr int STRAGGLER_WARPS_PER_SM = 32; // measured: 16 is slower, 64 no faster
 constexpr int STRAGGLER_WINDOW = 32; // nodes per window = one per lane
 
-struct __align__(16) StragglerWarpShared
+// What a warp needs to walk one ray through 32-node windows (1152 bytes).
+struct __align__(16) StragglerWindowShared
 {
     uint4         node[STRAGGLER_WINDOW]; // (tmin bits, a, b, flags)
     uint4         tri[STRAGGLER_WINDOW];  // first triangle of a leaf: (valid, u bits, v bits, t bits)
     std::uint32_t stack[RF_STACK_SIZE];
+};
+struct __align__(16) StragglerWarpShared : StragglerWindowShared
+{
     // bulk-copy mode: two staging buffers of one raw window each, filled by cp.async.bulk — [0] on demand, [1] ahead of time
     PackedNode         raw[2][STRAGGLER_WINDOW];
     unsigned long long barrier[2]; // their mbarriers
@@ -53,32 +57,29 @@ enum StragglerWindowMode : int
 constexpr std::uint32_t WIN_OK = 1u;  // tmin <= tmx && tmx > 0 (the tmax-independent part of the slab test)
 constexpr std::uint32_t WIN_NAN = 2u; // a slab product was NaN: re-test with the literal form at the visit
 
-// Traces the ray of `rec` to its end on the calling warp (all 32 lanes, converged) and returns its result in
-// (hit, rayNodes, rayTris) on every lane.
-template<int WINDOW_MODE, class IO>
-__device__ __forceinline__ void traceStragglerWarp(
+// Walks the ray `r` (warp-uniform: every lane holds the same values; its stack entries are in sh.stack[0, r.sp)) to its end
+// on the calling warp (all 32 lanes, converged) and hands the result to io.finish on lane 0.  Returns true when finish chained
+// another ray (e.g. a path's closest-hit ray right after its shadow ray): `r` then holds that ray, fresh, on every lane.
+// SH = StragglerWindowShared (DIRECT mode) or StragglerWarpShared.
+template<int WINDOW_MODE, class SH, class IO>
+__device__ __forceinline__ bool traceWarpRay(
     const PackedNode* __restrict__ nodes,
     const float4* __restrict__ tris,
-    const StragglerRecord* rec,
-    StragglerWarpShared&   sh,
-    std::uint32_t&         barrierParity, // bulk-copy mode: bit b = phase parity the next wait on sh.barrier[b] expects (kept by the caller across rays)
-    IO&                    io)
+    WarpRay&       r,
+    SH&            sh,
+    std::uint32_t& barrierParity, // bulk-copy mode: bit b = phase parity the next wait on sh.barrier[b] expects (kept by the caller across rays)
+    IO&            io)
 {
     const std::uint32_t lane = laneId();
-    // ---- the ray, as traceRays left it (uniform: every lane reads the same words) ------------------------------
-    const uint4 h0 = __ldcg(&rec->head[0]), h1 = __ldcg(&rec->head[1]), h2 = __ldcg(&rec->head[2]), h3 = __ldcg(&rec->head[3]),
-                h4 = __ldcg(&rec->head[4]);
-    if ((h0.y & 0xFFu) == 0u) return; // an empty slot (reserved by a warp that found the buffer full)
-    const std::uint32_t rayIdx = h0.x;
-    std::uint32_t       cur = h0.z, pendTri = h0.w, pendEnd = h1.x, rayNodes = h1.y, rayTris = h1.z;
-    float               tmax = __uint_as_float(h1.w);
-    const V3            o = v3(__uint_as_float(h2.x), __uint_as_float(h2.y), __uint_as_float(h2.z));
-    const V3            d = v3(__uint_as_float(h2.w), __uint_as_float(h3.x), __uint_as_float(h3.y));
-    HitRecord           hit{h3.z, __uint_as_float(h3.w), __uint_as_float(h4.x), __uint_as_float(h4.y)};
-    const int           state = static_cast<int>(h0.y & 0xFFu); // 1 NODE, 2 TRI, 3 DONE (traceRays)
-    const bool          anyHit = (h0.y & 0x100u) != 0u;
-    std::uint32_t       sp = h0.y >> 16;
-    if (lane < sp) sh.stack[lane] = __ldcg(reinterpret_cast<const std::uint32_t*>(rec->stack) + lane);
+    const std::uint32_t rayIdx = r.rayIdx;
+    std::uint32_t       cur = r.cur, pendTri = r.pendTri, pendEnd = r.pendEnd, rayNodes = r.rayNodes, rayTris = r.rayTris;
+    float               tmax = r.tmax;
+    const V3            o = r.o;
+    const V3            d = r.d;
+    HitRecord           hit = r.hit;
+    const int           state = r.state; // 1 NODE, 2 TRI, 3 DONE (traceRays)
+    const bool          anyHit = r.anyHit;
+    std::uint32_t       sp = r.sp;
     const float         ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
     const std::uint32_t negMask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
     __syncwarp();
@@ -94,17 +95,21 @@ __device__ __forceinline__ void traceStragglerWarp(
 
     // ---- bulk-copy mode: staging buffers and their barriers (one warp owns them; phases persist across rays) -----------
     constexpr std::uint32_t WINDOW_BYTES = STRAGGLER_WINDOW * sizeof(PackedNode);
-    const std::uint32_t     bar0 = sharedAddress(&sh.barrier[0]), bar1 = sharedAddress(&sh.barrier[1]);
+    std::uint32_t           bar0 = 0, bar1 = 0;
+    if constexpr (WINDOW_MODE == STRAGGLER_BULK) bar0 = sharedAddress(&sh.barrier[0]), bar1 = sharedAddress(&sh.barrier[1]);
     std::uint32_t           aheadBase = 0x80000000u; // window in flight into (or sitting in) raw[1]; none: 0x80000000
     const auto issueCopy = [&](const int buffer, const std::uint32_t first) {
         // every lane has finished reading the buffer (the caller synchronised the warp) before the copy overwrites it.  No
         // proxy fence here: it is needed after generic-proxy WRITES that the async proxy must see, not after reads — and on
         // sm_100a it costs an L1 invalidation (SYNCS.CCTL.IVALL), which made this kernel 7 % slower when it sat here.
-        if (lane == 0u)
+        if constexpr (WINDOW_MODE == STRAGGLER_BULK)
         {
-            const std::uint32_t bar = buffer ? bar1 : bar0;
-            mbarrierArriveExpectTx(bar, WINDOW_BYTES);
-            bulkCopyGlobalToShared(sharedAddress(&sh.raw[buffer][0]), nodes + first, WINDOW_BYTES, bar);
+            if (lane == 0u)
+            {
+                const std::uint32_t bar = buffer ? bar1 : bar0;
+                mbarrierArriveExpectTx(bar, WINDOW_BYTES);
+                bulkCopyGlobalToShared(sharedAddress(&sh.raw[buffer][0]), nodes + first, WINDOW_BYTES, bar);
+            }
         }
     };
     // Copy the window at `first` ahead of time if the second buffer is free.
@@ -123,7 +128,7 @@ __device__ __forceinline__ void traceStragglerWarp(
         ++tlWindows;
 #endif
         base = first;
-        if (WINDOW_MODE == STRAGGLER_BULK)
+        if constexpr (WINDOW_MODE == STRAGGLER_BULK)
         {
             const int buffer = aheadBase == first ? 1 : 0;
             if (buffer == 0) issueCopy(0, first);
@@ -265,10 +270,12 @@ __device__ __forceinline__ void traceStragglerWarp(
         while (!mbarrierTryWait(bar1, (barrierParity >> 1) & 1u)) {}
         barrierParity ^= 2u;
     }
-    V3    o2 = o, d2 = d;
-    float tmax2 = tmax;
-    bool  anyHit2 = anyHit;
-    if (lane == 0u) io.finish(rayIdx, hit.tri != RF_NO_HIT, hit, rayNodes, rayTris, anyHit, o2, d2, tmax2, anyHit2);
+    V3            o2 = o, d2 = d;
+    float         tmax2 = tmax;
+    bool          anyHit2 = anyHit;
+    std::uint32_t id2 = rayIdx;
+    int           chained = 0;
+    if (lane == 0u) chained = io.finish(id2, hit.tri != RF_NO_HIT, hit, rayNodes, rayTris, anyHit, o2, d2, tmax2, anyHit2) ? 1 : 0;
 #ifdef RF_TRACE_TIMELINE
     if (lane == 0u && g_timeline != nullptr)
     {
@@ -279,5 +286,46 @@ __device__ __forceinline__ void traceStragglerWarp(
     }
 #endif
     __syncwarp();
+    chained = __shfl_sync(0xFFFFFFFFu, chained, 0);
+    if (chained != 0)
+    {
+        r.rayIdx = __shfl_sync(0xFFFFFFFFu, id2, 0);
+        r.o = v3(__shfl_sync(0xFFFFFFFFu, o2.x, 0), __shfl_sync(0xFFFFFFFFu, o2.y, 0), __shfl_sync(0xFFFFFFFFu, o2.z, 0));
+        r.d = v3(__shfl_sync(0xFFFFFFFFu, d2.x, 0), __shfl_sync(0xFFFFFFFFu, d2.y, 0), __shfl_sync(0xFFFFFFFFu, d2.z, 0));
+        r.tmax = __shfl_sync(0xFFFFFFFFu, tmax2, 0);
+        r.anyHit = __shfl_sync(0xFFFFFFFFu, anyHit2 ? 1 : 0, 0) != 0;
+        r.cur = 0u, r.pendTri = 0u, r.pendEnd = 0u, r.rayNodes = 0u, r.rayTris = 0u, r.sp = 0u;
+        r.state = 1;
+        r.hit = HitRecord{RF_NO_HIT, 0.f, 0.f, 0.f};
+    }
+    return chained != 0;
+}
+
+// Traces the ray of `rec` (handed over by traceRays) to its end on the calling warp.
+template<int WINDOW_MODE, class IO>
+__device__ __forceinline__ void traceStragglerWarp(
+    const PackedNode* __restrict__ nodes,
+    const float4* __restrict__ tris,
+    const StragglerRecord* rec,
+    StragglerWarpShared&   sh,
+    std::uint32_t&         barrierParity,
+    IO&                    io)
+{
+    // the ray, as traceRays left it (uniform: every lane reads the same words)
+    const uint4 h0 = __ldcg(&rec->head[0]), h1 = __ldcg(&rec->head[1]), h2 = __ldcg(&rec->head[2]), h3 = __ldcg(&rec->head[3]),
+                h4 = __ldcg(&rec->head[4]);
+    if ((h0.y & 0xFFu) == 0u) return; // an empty slot (reserved by a warp that found the buffer full)
+    WarpRay r;
+    r.rayIdx = h0.x;
+    r.cur = h0.z, r.pendTri = h0.w, r.pendEnd = h1.x, r.rayNodes = h1.y, r.rayTris = h1.z;
+    r.tmax = __uint_as_float(h1.w);
+    r.o = v3(__uint_as_float(h2.x), __uint_as_float(h2.y), __uint_as_float(h2.z));
+    r.d = v3(__uint_as_float(h2.w), __uint_as_float(h3.x), __uint_as_float(h3.y));
+    r.hit = HitRecord{h3.z, __uint_as_float(h3.w), __uint_as_float(h4.x), __uint_as_float(h4.y)};
+    r.state = static_cast<int>(h0.y & 0xFFu);
+    r.anyHit = (h0.y & 0x100u) != 0u;
+    r.sp = h0.y >> 16;
+    if (laneId() < r.sp) sh.stack[laneId()] = __ldcg(reinterpret_cast<const std::uint32_t*>(rec->stack) + laneId());
+    while (traceWarpRay<WINDOW_MODE>(nodes, tris, r, sh, barrierParity, io)) {}
 }
 } // namespace rfb200

@@ -67,6 +67,17 @@ struct __align__(16) StragglerRecord
 };
 static_assert(sizeof(StragglerRecord) == 208, "13 x 16 B");
 
+// A ray in the form the warp-per-ray walk takes it (straggler.cuh): the same values on every lane.
+struct WarpRay
+{
+    std::uint32_t rayIdx, cur, pendTri, pendEnd, rayNodes, rayTris, sp; // sp: stack entries (in the walk's shared-memory stack)
+    int           state;                                              // 1 NODE, 2 TRI, 3 DONE
+    bool          anyHit;
+    float         tmax;
+    V3            o, d;
+    HitRecord     hit;
+};
+
 struct StragglerBuffer
 {
     StragglerRecord* records;
@@ -82,6 +93,8 @@ struct CursorSource
     // Straggler policy of the IO (compile time): false = every ray ends on the lane it started on; true = once the
     // queue is dry, warps with few rays left append them to `stragglers` and exit (the IO then has that member).
     static constexpr bool HANDS_OVER_STRAGGLERS = false;
+    // true = the caller goes on with the whole warp per ray once io.tailPhase() holds (see the end of traceRays' loop)
+    static constexpr bool WALKS_LAST_RAY_WITH_WARP = false;
 #ifdef RF_TRACE_TIMELINE
     __device__ __forceinline__ unsigned long long timelineTag() const { return reinterpret_cast<unsigned long long>(cursor); }
 #endif
@@ -104,6 +117,7 @@ struct TraceTuning
     std::uint32_t triMin;    // run a triangle round once this many lanes have a triangle pending
     std::uint32_t refillMin; // refill once this many lanes are idle
     std::uint32_t shadeWait; // persistent kernel: 0.5 us naps the shading warp takes to let a batch of 32 fill (mega.cuh)
+    std::uint32_t tailPaths; // persistent kernel: a block with this many live paths or fewer (and no pixels left to take) gives each of its rays a whole warp
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
@@ -290,8 +304,10 @@ __device__ __forceinline__ void traceRays(
     const bool          sceneOrdered,
     const TraceTuning   tuning,
     IO&                 io,
-    std::uint32_t*      externalStack = nullptr)
+    std::uint32_t*      externalStack = nullptr,
+    WarpRay*            leftover = nullptr) // IO::WALKS_LAST_RAY_WITH_WARP: the ray the warp still held when it left (state 0: none)
 {
+    if constexpr (IO::WALKS_LAST_RAY_WITH_WARP) leftover->state = 0;
     // Traversal stack: a [warp][entry][lane] shared array — entry k of this thread lives STACK_STRIDE * k bytes above
     // stackBase, bank = lane for every k, and the STACK x 128 bytes of a warp are contiguous.
     static_assert(STACK >= 1 && STACK <= RF_STACK_SIZE, "the reference's stack has 32 entries");
@@ -585,6 +601,45 @@ __device__ __forceinline__ void traceRays(
             }
         }
         if (exhausted && busyMask == 0u && !gotWork) break;
+        if constexpr (IO::WALKS_LAST_RAY_WITH_WARP)
+        {
+            // The end of a persistent kernel's frame: once the IO says that only a handful of rays are left, a warp that holds
+            // at most ONE ray leaves this loop, and its caller goes on ray by ray with all 32 lanes (straggler.cuh: 32-node
+            // windows, ~2.5x faster than a lone lane).  The ray's state leaves through `leftover` (shuffles), its stack through
+            // the first 32 words of row 8 of the warp's own stack memory (where StragglerWindowShared::stack lies).
+            if (sceneOrdered && io.tailPhase())
+            {
+                const unsigned walking = __ballot_sync(0xFFFFFFFFu, state == NODE || state == TRI);
+                const unsigned holding = __ballot_sync(0xFFFFFFFFu, state != IDLE);
+                if (holding == walking && (walking & (walking - 1u)) == 0u)
+                {
+                    if (walking != 0u)
+                    {
+                        const int src = __ffs(static_cast<int>(walking)) - 1;
+                        WarpRay&  r = *leftover;
+                        r.rayIdx = __shfl_sync(0xFFFFFFFFu, rayIdx, src);
+                        r.cur = __shfl_sync(0xFFFFFFFFu, cur, src);
+                        r.pendTri = __shfl_sync(0xFFFFFFFFu, pendTri, src), r.pendEnd = __shfl_sync(0xFFFFFFFFu, pendEnd, src);
+                        r.rayNodes = __shfl_sync(0xFFFFFFFFu, rayNodes, src), r.rayTris = __shfl_sync(0xFFFFFFFFu, rayTris, src);
+                        r.sp = __shfl_sync(0xFFFFFFFFu, (stackTop - stackBase) / STACK_STRIDE, src);
+                        r.state = __shfl_sync(0xFFFFFFFFu, state, src);
+                        r.anyHit = __shfl_sync(0xFFFFFFFFu, RF_ANY_HIT ? 1 : 0, src) != 0;
+                        r.tmax = __shfl_sync(0xFFFFFFFFu, tmax, src);
+                        r.o = v3(__shfl_sync(0xFFFFFFFFu, o.x, src), __shfl_sync(0xFFFFFFFFu, o.y, src), __shfl_sync(0xFFFFFFFFu, o.z, src));
+                        r.d = v3(__shfl_sync(0xFFFFFFFFu, d.x, src), __shfl_sync(0xFFFFFFFFu, d.y, src), __shfl_sync(0xFFFFFFFFu, d.z, src));
+                        r.hit.tri = __shfl_sync(0xFFFFFFFFu, hit.tri, src);
+                        r.hit.u = __shfl_sync(0xFFFFFFFFu, hit.u, src), r.hit.v = __shfl_sync(0xFFFFFFFFu, hit.v, src), r.hit.t = __shfl_sync(0xFFFFFFFFu, hit.t, src);
+                        // lane L fetches entry L of the ray's stack column, then parks it where the walk expects its stack
+                        const std::uint32_t column = __shfl_sync(0xFFFFFFFFu, stackBase, src);
+                        const std::uint32_t entry = laneId() < r.sp ? stackLoad(column + laneId() * STACK_STRIDE) : 0u;
+                        __syncwarp();
+                        stackMem[(threadIdx.x >> 5) * (STACK * 32) + 8 * 32 + laneId()] = entry;
+                        __syncwarp();
+                    }
+                    break;
+                }
+            }
+        }
         if constexpr (IO::HANDS_OVER_STRAGGLERS)
         {
           if (mayEvict && exhausted && !gotWork)
