@@ -191,7 +191,7 @@ typedef struct rf_frame_stats
                                     * node a ray entered (csrc/traversal_pairs.cuh), or one 32-byte node per visit with the
                                     * per-node kernel — the memory work behind the visits above */
     uint32_t trace_kernel;         /* traversal kernel in effect: 2 = child-pair records, 1 = one node per visit */
-    uint32_t reserved;
+    uint32_t persistent_kernel;    /* 1: frames run as one persistent launch (csrc/mega.cuh), 0: one launch per stage */
 } rf_frame_stats;
 
 /* ---- the renderer: nlrs::ReferencePathTracer (pt/reference_path_tracer.hpp:59-102) ------------- */
@@ -276,12 +276,19 @@ rf_status rf_renderer_set_stage_timing(rf_renderer* r, int32_t enabled);
  * are idle, `blocks_per_sm` persistent 256-thread blocks are launched per SM (automatic until set: 4, or 2 per tile set
  * for a small frame, see rf_renderer_set_pipeline).  0 keeps a value. */
 rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refill_min, uint32_t blocks_per_sm);
-/* How a frame is scheduled (results never depend on it).  sub_frames (1..4, 0 keeps, -1 automatic = the default: 2):
- * the frame is traced as that many independent tile sets on separate CUDA streams so one set's traversal tail overlaps
- * the other's work; when this GPU owns at most ~0.6 M pixels the automatic schedule also gives each set's traversal
- * launches half of the SM slots (both sets resident together) and turns the tail hand-over on.  persistent_kernel (0/1,
- * -1 keeps): experimental single-launch pipeline (csrc/mega.cuh) instead of one launch per stage.  variant (0..15, -1
- * keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling variant and block size of the traversal kernel. */
+/* How a frame is scheduled (results never depend on it).
+ * persistent_kernel (0 / 1 / 2, -1 keeps; 2 = automatic is the default): 1 = the whole frame of a tile set is ONE persistent
+ *   launch (csrc/mega.cuh): every block generates its own primary rays and keeps its paths to itself — ready rays of any
+ *   bounce wait in shared-memory rings, 7 (or 15) warps trace, one warp shades 32 hits at a time, a path's shadow ray and
+ *   next closest-hit ray run on the same lane, paths that lag behind are served first, and at the end of the frame a warp
+ *   walks its last ray with all 32 lanes.  Nothing waits for a bounce to finish, which is what a small frame needs: the
+ *   automatic schedule uses it when this GPU owns at most ~0.6 M pixels (a 1080p frame split over 4-8 GPUs) and the staged
+ *   pipeline (one launch per stage: raygen, trace, shade, ...) otherwise.
+ * sub_frames (1..4, 0 keeps, -1 automatic = the default): the frame is traced as that many independent tile sets on separate
+ *   CUDA streams.  Automatic: 1 with the persistent kernel; 2 with the staged pipeline, so that one set's traversal tail
+ *   overlaps the other's work.
+ * variant (0..15, -1 keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling variant and block size of the
+ *   staged traversal kernel (the persistent kernel's block size is the option "mega_block"). */
 rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t persistent_kernel, int32_t variant, int32_t block_threads);
 /* Tail policy of the traversal launches (results never depend on it).  Once a launch's ray queue is dry, a warp left
  * with <= evict_max rays keeps them for four more loop rounds (most of them are short and end there), then writes the
@@ -292,6 +299,12 @@ rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t p
 rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
 /* Named scheduling / debugging knobs (results never depend on them; unknown names are an error):
  *   "shade_wait"   persistent kernel: 0.5 us naps its shading warp takes to let a batch of 32 hits fill (default 16)
+ *   "mega_block"   persistent kernel: threads per block, 256 (4 blocks per SM, 7 traversal warps + 1 shading warp each; the
+ *                  default) or 512 (2 per SM, 15 + 1)
+ *   "mega_slots"   persistent kernel: path slots per block = paths a block keeps in flight (a multiple of 32, at most twice the
+ *                  block size; 0 = automatic: the block's share of the pixels, so that a small frame's paths all start at once)
+ *   "tail_paths"   persistent kernel: a block that has taken its last pixels and has at most n live paths left gives each ray a
+ *                  whole warp (value n + 1; 1 = never; 0 = automatic: two per traversal warp)
  *   "evict_delay"  loop rounds a warp keeps its last rays before handing them to the tail launch (default 4)
  *   "trace_stack"  force at least this many traversal-stack entries (<= 32; 0 = what the scene needs, the default)
  *   "trace_kernel" 0 / 1: traversal over 32-byte nodes, one per visit (csrc/traversal.cuh; the default); 2: over 64-byte
@@ -301,8 +314,7 @@ rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
  *   "tail_window_mode" how the warp-per-ray tail kernel fetches its 32-node windows: 0 = one LDG.256 per lane; 1 = one
  *                  1 KB bulk asynchronous copy (cp.async.bulk + mbarrier) into shared memory, with the window of the newest
  *                  out-of-window stack entry copied ahead of time while the current window is walked (csrc/straggler.cuh)
- *   "stage_debug"  1: print the per-launch spans of every stage-timed frame to stderr
- *   "mega_debug"   1: print the persistent kernel's control block after every frame (synchronises) */
+ *   "stage_debug"  1: print the per-launch spans of every stage-timed frame to stderr */
 rf_status rf_renderer_set_option(rf_renderer* r, const char* name, int64_t value);
 
 /* ---- the deferred renderer's lighting + resolve passes as a second integrator -------

@@ -89,7 +89,7 @@ class FrameStats(C.Structure):
                 ("shadow_triangles_tested", C.c_uint64), ("device_ms_total", C.c_double),
                 ("device_ms_trace", C.c_double), ("device_ms_shade", C.c_double), ("device_ms_other", C.c_double),
                 ("kernel_launches", C.c_uint64), ("sub_frames", C.c_uint32), ("evict_max", C.c_uint32),
-                ("node_records_loaded", C.c_uint64), ("trace_kernel", C.c_uint32), ("reserved", C.c_uint32)]
+                ("node_records_loaded", C.c_uint64), ("trace_kernel", C.c_uint32), ("persistent_kernel", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/rayfinder_b200.h declares.

@@ -350,7 +350,10 @@ struct rf_renderer
     std::uint64_t kernelLaunches = 0;   // kernels launched by render() since the last reset_stats
     int         numSubFrames = 2;       // in effect (updateTiles)
     int         requestedSubFrames = 0; // 0: automatic
-    bool        megakernel = false; // the frame as one persistent kernel with block-local path loops (mega.cuh)
+    // The frame as one persistent kernel with block-local path loops (mega.cuh): 0 never, 1 always, 2 automatic = when this GPU
+    // owns at most ~0.6 M pixels (a 1080p frame split over 4-8 GPUs), where a staged traversal launch is mostly tail (measured
+    // on one B200: 672x384 2.47 vs 3.18 ms, 960x540 4.85 vs 5.14 ms; the full 1080p frame 17.3 vs 15.9 ms).
+    int         megaMode = 2;
     cudaEvent_t forkEvent = nullptr;
 
     rf_render_parameters params{};
@@ -483,7 +486,7 @@ struct rf_renderer
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) ++ownedTileCount;
-        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : 2;
+        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : (useMega() ? 1 : 2);
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) owned[k++ % static_cast<std::uint32_t>(numSubFrames)].push_back(ty * tilesX + tx);
@@ -542,11 +545,12 @@ struct rf_renderer
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
+    bool          useMega() const { return megaMode == 1 || (megaMode == 2 && smallFrame()); }
     std::uint32_t stragglerCapacity() const { return static_cast<std::uint32_t>(numSms) * 64u * 8u; }
     // (the tail hand-over belongs to the per-node kernel; the pair kernel ends every ray on its lane)
     std::uint32_t effectiveEvictMax() const
     {
-        if (usePairs() && !megakernel) return 0u;
+        if (usePairs() && !useMega()) return 0u;
         return evictMax >= 0 ? static_cast<std::uint32_t>(evictMax) : (smallFrame() ? 8u : 0u);
     }
 };
@@ -765,7 +769,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
     RF_CUDA(cudaEventRecord(r->forkEvent, s));
 
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->effectiveBlocksPerSm()) : r->gridFor(r->effectiveBlocksPerSm() * (256 / r->traceBlock));
+    const int gridTrace = r->usePairs() && !r->useMega() ? r->gridFor(r->effectiveBlocksPerSm()) : r->gridFor(r->effectiveBlocksPerSm() * (256 / r->traceBlock));
     RF_CUDA(stageMark());
     for (int i = 0; i < r->numSubFrames; ++i)
     {
@@ -778,7 +782,7 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
         std::uint32_t* ctr = sf.counters.ptr;
         RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(fp.numBounces) * sizeof(std::uint32_t), ss));
         std::uint32_t* const cursors = ctr + fp.numBounces + 1u;
-        if (r->megakernel && !staged)
+        if (r->useMega() && !staged)
         {
             // One launch for the tile set's whole frame (mega.cuh): all SM slots divided among the tile sets, and as many path
             // slots per block as the block's share of the pixels needs (every path in flight from the start: the paths of a
@@ -965,7 +969,7 @@ extern "C" rf_status rf_renderer_render_deferred_lighting(
     std::uint32_t* const cursors = ctr + 2;
     const StragglerBuffer noHandOver{nullptr, nullptr, 0u, 0u, 0u};
     const int gridLight = r->gridFor(8);
-    const int gridTrace = r->usePairs() && !r->megakernel ? r->gridFor(r->effectiveBlocksPerSm()) : r->gridFor(r->effectiveBlocksPerSm() * (256 / r->traceBlock));
+    const int gridTrace = r->usePairs() && !r->useMega() ? r->gridFor(r->effectiveBlocksPerSm()) : r->gridFor(r->effectiveBlocksPerSm() * (256 / r->traceBlock));
     RF_CUDA(cudaMemsetAsync(ctr, 0, counterSlots(1) * sizeof(std::uint32_t), s));
     k_deferred_primary<<<gridLight, BLOCK_THREADS, 0, s>>>(fp, scene, un, d.albedo.ptr, d.normal.ptr, d.depth.ptr, queues[0], &ctr[0], r->radiance.ptr, r->stats.ptr);
     // shadow rays of the G-buffer surfaces + the bounce rays
@@ -1112,9 +1116,10 @@ extern "C" rf_status rf_renderer_get_stats(rf_renderer* r, rf_frame_stats* out)
     out->device_ms_other = r->msOther;
     out->kernel_launches = r->kernelLaunches;
     out->sub_frames = static_cast<std::uint32_t>(r->numSubFrames);
-    out->evict_max = r->megakernel ? 0u : r->effectiveEvictMax();
+    out->evict_max = r->useMega() ? 0u : r->effectiveEvictMax();
     out->node_records_loaded = s[STAT_RECORDS];
-    out->trace_kernel = r->usePairs() && !r->megakernel ? 2u : 1u;
+    out->trace_kernel = r->usePairs() && !r->useMega() ? 2u : 1u;
+    out->persistent_kernel = r->useMega() ? 1u : 0u;
     if (s[STAT_FAILED] != 0ull) return setError(RF_ERROR_CUDA, "The persistent kernel left a frame on its watchdog (a lost path); the image is incomplete.");
     return RF_OK;
 }
@@ -1268,10 +1273,10 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
 extern "C" rf_status rf_renderer_set_pipeline(rf_renderer* r, std::int32_t subFrames, std::int32_t persistentKernel, std::int32_t variant, std::int32_t blockThreads)
 {
     if (!r) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_pipeline: null renderer");
-    if (subFrames > rf_renderer::MAX_SUBFRAMES || variant > 15 || (blockThreads != 0 && blockThreads != 64 && blockThreads != 128 && blockThreads != 256))
+    if (subFrames > rf_renderer::MAX_SUBFRAMES || persistentKernel > 2 || variant > 15 || (blockThreads != 0 && blockThreads != 64 && blockThreads != 128 && blockThreads != 256))
         return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_pipeline: value out of range");
     if (subFrames != 0 && (subFrames < 0 ? 0 : subFrames) != r->requestedSubFrames) r->requestedSubFrames = subFrames < 0 ? 0 : subFrames, r->tilesDirty = true;
-    if (persistentKernel >= 0) r->megakernel = persistentKernel != 0;
+    if (persistentKernel >= 0 && persistentKernel != r->megaMode) r->megaMode = persistentKernel, r->tilesDirty = true;
     if (variant >= 0) r->variant = variant;
     if (blockThreads > 0) r->traceBlock = blockThreads;
     return RF_OK;
