@@ -279,7 +279,7 @@ rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refi
 /* How a frame is scheduled (results never depend on it).
  * persistent_kernel (0 / 1 / 2, -1 keeps; 2 = automatic is the default): 1 = the whole frame of a tile set is ONE persistent
  *   launch (csrc/mega.cuh): every block generates its own primary rays and keeps its paths to itself — ready rays of any
- *   bounce wait in shared-memory rings, 7 (or 15) warps trace, one warp shades 32 hits at a time, a path's shadow ray and
+ *   bounce wait in shared-memory rings, 15 (or 7) warps trace, one warp shades 32 hits at a time, a path's shadow ray and
  *   next closest-hit ray run on the same lane, paths that lag behind are served first, and at the end of the frame a warp
  *   walks its last ray with all 32 lanes.  Nothing waits for a bounce to finish, which is what a small frame needs: the
  *   automatic schedule uses it when this GPU owns at most ~0.6 M pixels (a 1080p frame split over 4-8 GPUs) and the staged
@@ -299,8 +299,8 @@ rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t p
 rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
 /* Named scheduling / debugging knobs (results never depend on them; unknown names are an error):
  *   "shade_wait"   persistent kernel: 0.5 us naps its shading warp takes to let a batch of 32 hits fill (default 16)
- *   "mega_block"   persistent kernel: threads per block, 256 (4 blocks per SM, 7 traversal warps + 1 shading warp each; the
- *                  default) or 512 (2 per SM, 15 + 1)
+ *   "mega_block"   persistent kernel: threads per block, 512 (2 blocks per SM, 15 traversal warps + 1 shading warp each; the
+ *                  default) or 256 (4 per SM, 7 + 1)
  *   "mega_slots"   persistent kernel: path slots per block = paths a block keeps in flight (a multiple of 32, at most twice the
  *                  block size; 0 = automatic: the block's share of the pixels, so that a small frame's paths all start at once)
  *   "tail_paths"   persistent kernel: a block that has taken its last pixels and has at most n live paths left gives each ray a

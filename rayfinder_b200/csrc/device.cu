@@ -352,7 +352,7 @@ struct rf_renderer
     int         requestedSubFrames = 0; // 0: automatic
     // The frame as one persistent kernel with block-local path loops (mega.cuh): 0 never, 1 always, 2 automatic = when this GPU
     // owns at most ~0.6 M pixels (a 1080p frame split over 4-8 GPUs), where a staged traversal launch is mostly tail (measured
-    // on one B200: 672x384 2.47 vs 3.18 ms, 960x540 4.85 vs 5.14 ms; the full 1080p frame 17.3 vs 15.9 ms).
+    // on one B200: 672x384 2.42 vs 3.18 ms, 960x540 4.72 vs 5.14 ms, 1360x768 8.84 vs 8.72 ms, the full 1080p frame 16.5 vs 15.9 ms).
     int         megaMode = 2;
     cudaEvent_t forkEvent = nullptr;
 
@@ -540,7 +540,9 @@ struct rf_renderer
     std::uint32_t evictDelay = 4; // rounds a warp keeps its last rays before handing them over (measured: 4 lets the many short ones end in place)
     bool          stageDebug = false;
     std::uint32_t megaSlots = 0; // path slots per block of the persistent kernel (0: automatic; option "mega_slots")
-    int           megaBlock = 256; // threads per block of the persistent kernel (256 or 512; option "mega_block")
+    // threads per block of the persistent kernel (option "mega_block"): 512 = 2 blocks per SM with 15 traversal warps + 1 shading
+    // warp each (measured 2.42 / 4.72 / 16.5 ms at 672x384 / 960x540 / 1080p); 256 = 4 per SM with 7 + 1 (2.47 / 4.92 / 17.6 ms)
+    int           megaBlock = 512;
     int           stragglerWindowMode = STRAGGLER_DIRECT; // how the tail kernel fetches its node windows (straggler.cuh)
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;

@@ -383,6 +383,43 @@ def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames, window
     assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
 
 
+@pytest.mark.parametrize("block,slots,tail_paths,sub_frames,shade_wait", [
+    (512, 0, 0, -1, 16), (256, 0, 0, 1, 16), (256, 64, 1, 1, 0), (512, 96, 401, 2, 4), (256, 512, 2, 3, 64), (512, 1024, 31, 1, 16)])
+def test_sponza_persistent_kernel_is_exact(sponza_pt, block, slots, tail_paths, sub_frames, shade_wait):
+    """The frame as one persistent launch (csrc/mega.cuh): block-local path records, shared-memory ready / hit rings, a
+    path's shadow ray and next closest-hit ray on one lane with the shadow result folded in by the shading warp, lagging
+    paths first, and whole-warp walks of the last rays (rays moved from a lane to the warp in mid-traversal).  Block size,
+    path slots per block (few slots: pixels are taken as paths end; many: the whole share starts at once), the tail
+    threshold (off, always, early) and the batching wait change the schedule, never a counter or a pixel of the staged
+    pipeline's frame — on the scene whose grazing rays and axis-parallel shadow rays exercise the tail and the NaN re-test."""
+    w, h, bounces = 480, 270, 8
+    cam = rf.fly_camera(w, h)
+    ren, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+    ren.set_option("trace_kernel", 1)
+    ren.set_pipeline(1, 0, 3, 256)
+    ren.set_tail_policy(0)
+    ren.render(), ren.render()
+    ref_img, _ = ren.read_hdr()
+    ref_stats = ren.stats()
+    assert ref_stats["persistent_kernel"] == 0 and ref_stats["sub_frames"] == 1
+    ren2, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+    if sub_frames < 0:
+        assert ren2.stats()["persistent_kernel"] == 1  # the automatic schedule of a frame this small
+    ren2.set_pipeline(sub_frames, 2 if sub_frames < 0 else 1, -1, 0)
+    ren2.set_option("mega_block", block)
+    ren2.set_option("mega_slots", slots)
+    ren2.set_option("tail_paths", tail_paths)
+    ren2.set_option("shade_wait", shade_wait)
+    ren2.render(), ren2.render()
+    img, _ = ren2.read_hdr()
+    stats = ren2.stats()
+    assert stats["persistent_kernel"] == 1 and stats["sub_frames"] == (1 if sub_frames < 0 else sub_frames)
+    assert stats["kernel_launches"] == 2 * 2 * stats["sub_frames"]  # per frame and tile set: the persistent launch + the accumulation
+    for key in O.COUNTER_NAMES:
+        assert stats[key] == ref_stats[key], key
+    assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
+
+
 def test_click_to_focus_matches_reference_formula(duck_pt):
     """pt/main.cpp:198-226: ray through the cursor, rayIntersectBvh(..., 1000.f, ...), dot(hit.p - position, forward)."""
     f32 = np.float32
