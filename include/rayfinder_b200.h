@@ -282,7 +282,7 @@ rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refi
  *   bounce wait in shared-memory rings, 15 (or 7) warps trace, one warp shades 32 hits at a time, a path's shadow ray and
  *   next closest-hit ray run on the same lane, paths that lag behind are served first, and at the end of the frame a warp
  *   walks its last ray with all 32 lanes.  Nothing waits for a bounce to finish, which is what a small frame needs: the
- *   automatic schedule uses it when this GPU owns at most ~0.6 M pixels (a 1080p frame split over 4-8 GPUs) and the staged
+ *   automatic schedule uses it when this GPU owns at most ~1.2 M pixels (a 1080p frame split over 2-8 GPUs) and the staged
  *   pipeline (one launch per stage: raygen, trace, shade, ...) otherwise.
  * sub_frames (1..4, 0 keeps, -1 automatic = the default): the frame is traced as that many independent tile sets on separate
  *   CUDA streams.  Automatic: 1 with the persistent kernel; 2 with the staged pipeline, so that one set's traversal tail
@@ -301,8 +301,9 @@ rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
  *   "shade_wait"   persistent kernel: 0.5 us naps its shading warp takes to let a batch of 32 hits fill (default 16)
  *   "mega_block"   persistent kernel: threads per block, 512 (2 blocks per SM, 15 traversal warps + 1 shading warp each; the
  *                  default) or 256 (4 per SM, 7 + 1)
- *   "mega_slots"   persistent kernel: path slots per block = paths a block keeps in flight (a multiple of 32, at most twice the
- *                  block size; 0 = automatic: the block's share of the pixels, so that a small frame's paths all start at once)
+ *   "mega_slots"   persistent kernel: path slots per block = paths a block keeps in flight (a multiple of 32, at most four times
+ *                  the block size; 0 = automatic: the block's share of the pixels, so that a small frame's paths all start at
+ *                  once, or that share split into equal waves when it exceeds the maximum)
  *   "tail_paths"   persistent kernel: a block that has taken its last pixels and has at most n live paths left gives each ray a
  *                  whole warp (value n + 1; 1 = never; 0 = automatic: two per traversal warp)
  *   "evict_delay"  loop rounds a warp keeps its last rays before handing them to the tail launch (default 4)

@@ -351,8 +351,9 @@ struct rf_renderer
     int         numSubFrames = 2;       // in effect (updateTiles)
     int         requestedSubFrames = 0; // 0: automatic
     // The frame as one persistent kernel with block-local path loops (mega.cuh): 0 never, 1 always, 2 automatic = when this GPU
-    // owns at most ~0.6 M pixels (a 1080p frame split over 4-8 GPUs), where a staged traversal launch is mostly tail (measured
-    // on one B200: 672x384 2.42 vs 3.18 ms, 960x540 4.72 vs 5.14 ms, 1360x768 8.84 vs 8.72 ms, the full 1080p frame 16.5 vs 15.9 ms).
+    // owns at most ~1.2 M pixels (a 1080p frame split over 2-8 GPUs), where the ends of the staged pipeline's nine traversal
+    // launches weigh most (measured on one B200, persistent vs staged: 672x384 2.42 vs 3.18 ms, 960x540 4.37 vs 5.14 ms,
+    // 1360x768 8.49 vs 8.72 ms; the full 1080p frame 16.5 vs 15.9 ms).
     int         megaMode = 2;
     cudaEvent_t forkEvent = nullptr;
 
@@ -547,7 +548,7 @@ struct rf_renderer
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
-    bool          useMega() const { return megaMode == 1 || (megaMode == 2 && smallFrame()); }
+    bool          useMega() const { return megaMode == 1 || (megaMode == 2 && static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 1200000ull); }
     std::uint32_t stragglerCapacity() const { return static_cast<std::uint32_t>(numSms) * 64u * 8u; }
     // (the tail hand-over belongs to the per-node kernel; the pair kernel ends every ray on its lane)
     std::uint32_t effectiveEvictMax() const
@@ -792,8 +793,12 @@ extern "C" rf_status rf_renderer_render(rf_renderer* r)
             const int           megaGrid = r->gridFor(r->traceBlocksPerSm > 0 ? r->traceBlocksPerSm : std::max(1, 4 / r->numSubFrames)) * 256 / r->megaBlock;
             const std::uint64_t pathsPerBlock = (static_cast<std::uint64_t>(sf.numOwnedTiles) * TILE_PIXELS + megaGrid - 1) / megaGrid;
             const std::uint32_t maxSlots = loopMaxSlots(r->megaBlock);
+            // Path slots per block.  Paths that cannot start at once start as others end, in "waves"; a last wave that is only
+            // partly filled leaves lanes idle for a whole path's latency (measured at 960x540: 1760 slots for 1750 paths per block
+            // 4.37 ms, 1536 slots 5.05 ms), so the share is split into the fewest waves that fit, all of the same size.
+            const std::uint64_t waves = (pathsPerBlock + maxSlots - 1) / maxSlots;
             const std::uint32_t slots = r->megaSlots != 0u ? std::min(r->megaSlots, maxSlots)
-                                                           : static_cast<std::uint32_t>(std::min<std::uint64_t>(maxSlots, std::max<std::uint64_t>(r->megaBlock, (pathsPerBlock + 31u) & ~31ull)));
+                                                           : static_cast<std::uint32_t>(std::max<std::uint64_t>(64u, ((pathsPerBlock + waves - 1) / waves + 31u) & ~31ull));
             const std::uint64_t recordSlots = static_cast<std::uint64_t>(megaGrid) * slots;
             if (recordSlots > sf.pathRecordSlots)
             {
@@ -1266,7 +1271,7 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
     else if (key == "pair_variant" && value <= 7) r->pairVariant = static_cast<int>(value);
     else if (key == "tail_window_mode" && value <= 1) r->stragglerWindowMode = static_cast<int>(value);
     else if (key == "stage_debug") r->stageDebug = value != 0;
-    else if (key == "mega_slots" && (value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0))) r->megaSlots = static_cast<std::uint32_t>(value);
+    else if (key == "mega_slots" && (value == 0 || (value >= 64 && value <= 2048 && value % 32 == 0))) r->megaSlots = static_cast<std::uint32_t>(value);
     else if (key == "mega_block" && (value == 256 || value == 512)) r->megaBlock = static_cast<int>(value);
     else return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: unknown option '%s'", name);
     return RF_OK;

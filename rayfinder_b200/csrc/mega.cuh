@@ -31,9 +31,10 @@
 
 namespace rfb200
 {
-// Per block of BLOCK threads: up to 2 x BLOCK path slots (the launch picks how many are used), ready rings of the same
-// capacity (so they can never overflow), a hit ring of BLOCK / 2 entries (every KB of shared memory is a KB less L1).
-__host__ __device__ constexpr std::uint32_t loopMaxSlots(const int block) { return 2u * static_cast<std::uint32_t>(block); }
+// Per block of BLOCK threads: up to 4 x BLOCK path slots (the launch picks how many are used), a ready ring of the same
+// capacity (it can never overflow) plus one of BLOCK entries for the paths served first, a hit ring of BLOCK / 2 entries
+// (every KB of shared memory is a KB less L1).
+__host__ __device__ constexpr std::uint32_t loopMaxSlots(const int block) { return 4u * static_cast<std::uint32_t>(block); }
 constexpr std::uint32_t LOOP_LEVELS = 16;       // bounce levels told apart by the scheduling priority (deeper ones share the last)
 constexpr std::uint32_t LOOP_RECORD_VEC = 6;    // float4 per path record
 
@@ -46,24 +47,27 @@ constexpr int REC_CONTRIBUTION = 4; // throughput * lightIntensity * reflectance
 constexpr int REC_RADIANCE = 5;
 
 // ready-ring entry (16 bit): slot | flags
-constexpr std::uint32_t LOOP_SLOT_MASK = 1023u;
-constexpr std::uint32_t READY_SHADOW = 1u << 10;  // trace the shadow ray first
-constexpr std::uint32_t READY_CLOSEST = 1u << 11; // trace the closest-hit ray (after the shadow ray, if any)
+constexpr std::uint32_t LOOP_SLOT_MASK = 4095u;
+constexpr std::uint32_t READY_SHADOW = 1u << 12;  // trace the shadow ray first
+constexpr std::uint32_t READY_CLOSEST = 1u << 13; // trace the closest-hit ray (after the shadow ray, if any)
 // what a traversal lane carries for its ray (traceRays' rayIdx), and word 0 of a hit-ring entry
-constexpr std::uint32_t LANE_CLOSEST_FOLLOWS = 1u << 11;
-constexpr std::uint32_t LANE_HAD_SHADOW = 1u << 12; // the path's shadow ray was traced on this lane just before ...
-constexpr std::uint32_t LANE_SHADOW_HIT = 1u << 13; // ... and was blocked
-constexpr std::uint32_t LANE_FINAL = 1u << 14;      // no closest-hit result in this entry: the path ends with its shadow ray
+constexpr std::uint32_t LANE_CLOSEST_FOLLOWS = 1u << 13;
+constexpr std::uint32_t LANE_HAD_SHADOW = 1u << 14; // the path's shadow ray was traced on this lane just before ...
+constexpr std::uint32_t LANE_SHADOW_HIT = 1u << 15; // ... and was blocked
+constexpr std::uint32_t LANE_FINAL = 1u << 16;      // no closest-hit result in this entry: the path ends with its shadow ray
 
 template<int BLOCK>
 struct PathLoopShared
 {
     static constexpr int WARPS = BLOCK / 32;
-    static constexpr std::uint32_t MAX_SLOTS = loopMaxSlots(BLOCK), READY_CAP = MAX_SLOTS, HIT_CAP = BLOCK / 2;
-    static_assert(MAX_SLOTS <= LOOP_SLOT_MASK + 1u && (HIT_CAP & (HIT_CAP - 1u)) == 0u && (READY_CAP & (READY_CAP - 1u)) == 0u, "slot bits / ring capacities");
+    static constexpr std::uint32_t MAX_SLOTS = loopMaxSlots(BLOCK), READY_CAP = MAX_SLOTS, URGENT_CAP = BLOCK, HIT_CAP = BLOCK / 2;
+    static_assert(MAX_SLOTS <= LOOP_SLOT_MASK + 1u && (HIT_CAP & (HIT_CAP - 1u)) == 0u && (READY_CAP & (READY_CAP - 1u)) == 0u && (URGENT_CAP & (URGENT_CAP - 1u)) == 0u,
+                  "slot bits / ring capacities");
+    __host__ __device__ static constexpr std::uint32_t ringCap(const std::uint32_t ring) { return ring == 0u ? URGENT_CAP : READY_CAP; }
     uint4          hitRing[HIT_CAP];    // (lane word, tri, u, v) of finished closest-hit rays
     std::uint32_t  hitSeq[HIT_CAP];     // lap tag of the entry (position / CAP + 1), written after the entry
-    std::uint16_t  readyRing[2][READY_CAP]; // [0]: paths that lag behind the others of the block (served first), [1]: the rest
+    std::uint16_t  urgentRing[URGENT_CAP];   // ready ring 0: paths that lag behind the others of the block, served first (when it is full they queue with the rest)
+    std::uint16_t  readyRing[READY_CAP];     // ready ring 1: the rest
     std::uint16_t  freeStack[MAX_SLOTS]; // private to the shading warp
     std::uint16_t  grant[WARPS][32];         // entries a traversal warp has just reserved (acquire -> fetch)
     std::uint32_t  hitTail;                  // reserved positions (traversal lanes, atomicAdd)
@@ -128,7 +132,11 @@ struct PathLoopIO
             ring = __shfl_sync(0xFFFFFFFFu, ring, 0);
             if (n == 0u) break;
             std::uint16_t entry = 0;
-            if (laneId() < n) entry = *reinterpret_cast<const volatile std::uint16_t*>(&sh.readyRing[ring][(head + laneId()) & (PathLoopShared<BLOCK>::READY_CAP - 1u)]);
+            if (laneId() < n)
+            {
+                const std::uint16_t* slots = ring == 0u ? sh.urgentRing : sh.readyRing;
+                entry = *reinterpret_cast<const volatile std::uint16_t*>(&slots[(head + laneId()) & (Shared::ringCap(ring) - 1u)]);
+            }
             std::uint32_t won = 0;
             if (laneId() == 0u) won = atomicCAS(&sh.readyHead[ring], head, head + n) == head ? 1u : 0u;
             won = __shfl_sync(0xFFFFFFFFu, won, 0);
@@ -371,14 +379,23 @@ __device__ __forceinline__ void pathLoopShadeWarp(
     const auto publish = [&](const bool pred, const std::uint32_t entry, const std::uint32_t level) {
         if (__ballot_sync(0xFFFFFFFFu, pred) == 0u) return;
         const std::uint32_t minLevel = leastAdvancedLevel();
-        const bool          urgent = level <= minLevel + 1u;
-#pragma unroll
-        for (std::uint32_t ring = 0; ring < 2u; ++ring)
+        bool                urgent = level <= minLevel + 1u;
+        // the urgent ring is small: what does not fit queues with the rest (harmless: when many paths are urgent, none is)
+        std::uint32_t room = 0;
+        if (lane == 0u) room = PathLoopShared<BLOCK>::URGENT_CAP - (readyTail[0] - volatileLoad(&sh.readyHead[0]));
+        room = __shfl_sync(0xFFFFFFFFu, room, 0);
+        if (static_cast<std::uint32_t>(__popc(__ballot_sync(0xFFFFFFFFu, pred && urgent))) > room) urgent = false;
         {
-            const bool     mine = pred && (urgent ? 0u : 1u) == ring;
+            const bool     mine = pred && urgent;
             const unsigned mask = __ballot_sync(0xFFFFFFFFu, mine);
-            if (mine) sh.readyRing[ring][(readyTail[ring] + static_cast<std::uint32_t>(__popc(mask & lanesBelow))) & (PathLoopShared<BLOCK>::READY_CAP - 1u)] = static_cast<std::uint16_t>(entry);
-            readyTail[ring] += static_cast<std::uint32_t>(__popc(mask));
+            if (mine) sh.urgentRing[(readyTail[0] + static_cast<std::uint32_t>(__popc(mask & lanesBelow))) & (PathLoopShared<BLOCK>::URGENT_CAP - 1u)] = static_cast<std::uint16_t>(entry);
+            readyTail[0] += static_cast<std::uint32_t>(__popc(mask));
+        }
+        {
+            const bool     mine = pred && !urgent;
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, mine);
+            if (mine) sh.readyRing[(readyTail[1] + static_cast<std::uint32_t>(__popc(mask & lanesBelow))) & (PathLoopShared<BLOCK>::READY_CAP - 1u)] = static_cast<std::uint16_t>(entry);
+            readyTail[1] += static_cast<std::uint32_t>(__popc(mask));
         }
         __threadfence(); // the path records (global) and the ring entries before the tails
         __syncwarp();
