@@ -282,8 +282,9 @@ rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refi
  *   bounce wait in shared-memory rings, 15 (or 7) warps trace, one warp shades 32 hits at a time, a path's shadow ray and
  *   next closest-hit ray run on the same lane, paths that lag behind are served first, and at the end of the frame a warp
  *   walks its last ray with all 32 lanes.  Nothing waits for a bounce to finish, which is what a small frame needs: the
- *   automatic schedule uses it when this GPU owns at most ~1.2 M pixels (a 1080p frame split over 2-8 GPUs) and the staged
- *   pipeline (one launch per stage: raygen, trace, shade, ...) otherwise.
+ *   automatic schedule uses it when this GPU owns at most ~1.2 M pixels (a 1080p frame split over 2-8 GPUs) and paths have at
+ *   least 6 bounces (3 between 0.15 M and 0.6 M pixels), and the staged pipeline (one launch per stage: raygen, trace, shade,
+ *   ...) otherwise.
  * sub_frames (1..4, 0 keeps, -1 automatic = the default): the frame is traced as that many independent tile sets on separate
  *   CUDA streams.  Automatic: 1 with the persistent kernel; 2 with the staged pipeline, so that one set's traversal tail
  *   overlaps the other's work.

@@ -459,7 +459,9 @@ struct rf_renderer
         const rf_status st = rf_sky_state_new(&p.sky, &newSky);
         if (st != RF_OK) return st;
         skyState = newSky;
-        if (p.framebuffer_width != params.framebuffer_width || p.framebuffer_height != params.framebuffer_height) tilesDirty = true;
+        if (p.framebuffer_width != params.framebuffer_width || p.framebuffer_height != params.framebuffer_height ||
+            p.sampling_params.num_bounces != params.sampling_params.num_bounces)
+            tilesDirty = true; // (the automatic schedule depends on both)
         params = p;
         accumulated = 0; // reset the temporal accumulation (reference_path_tracer.cpp:561)
         // Sampling tables for every n = frameCount % numSamplesPerPixel.
@@ -548,7 +550,17 @@ struct rf_renderer
     int           evictMax = -1; // -1: automatic
     std::uint32_t ownedTileCount = 0;
     bool          smallFrame() const { return static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 600000ull; }
-    bool          useMega() const { return megaMode == 1 || (megaMode == 2 && static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS <= 1200000ull); }
+    // Automatic: the persistent kernel pays where a frame is many short launches — few pixels per GPU AND several bounces.  With one
+    // or two bounces the staged pipeline has only two or three launches, the first of them over coherent primary rays, and stays
+    // ahead (1024^2: 1.00 vs 1.17 ms at 1 bounce, 4.64 vs 4.76 ms at 4, 8.83 vs 8.65 ms at 8; 512^2: 0.87 vs 0.85 ms at 2 bounces,
+    // 1.76 vs 1.43 ms at 4; profiles/r02_sweep_1gpu.json against r01b_sweep_1gpu.json).
+    bool          useMega() const
+    {
+        if (megaMode != 2) return megaMode == 1;
+        const std::uint64_t pixels = static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS;
+        const std::uint32_t bounces = params.sampling_params.num_bounces;
+        return pixels <= 1200000ull && (bounces >= 6u || (bounces >= 3u && pixels > 150000ull && pixels <= 600000ull));
+    }
     std::uint32_t stragglerCapacity() const { return static_cast<std::uint32_t>(numSms) * 64u * 8u; }
     // (the tail hand-over belongs to the per-node kernel; the pair kernel ends every ray on its lane)
     std::uint32_t effectiveEvictMax() const
