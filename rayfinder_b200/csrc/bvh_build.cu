@@ -47,7 +47,8 @@ enum NodeKind : std::uint32_t
     KIND_LEAF = 1,
     KIND_SPLIT2 = 2,  // two primitives: median split, done in the decide step
     KIND_SAH = 3,     // waiting for its bucket sweep
-    KIND_SPLIT = 4    // SAH split chosen: partition pending / done
+    KIND_SPLIT = 4,   // SAH split chosen: partition pending / done
+    KIND_DEFERRED = 5 // single-launch build: a small subtree taken out of the level-by-level flow; one block builds it on its own
 };
 
 struct BuildNode
@@ -59,8 +60,10 @@ struct BuildNode
     std::uint32_t bucketSlot;     // SAH: index into the bucket accumulators of the level
     std::uint32_t splitBucket;    // SAH: primitives of buckets <= splitBucket go left
     std::uint32_t mid;            // first position of the second child
-    std::uint32_t size;           // nodes in the subtree
-    std::uint32_t preorder;       // final node index
+    std::uint32_t size;           // nodes in the subtree            } level-by-level path only
+    std::uint32_t preorder;       // final node index                }
+    std::uint32_t depth;          // ancestors
+    std::uint32_t rightTurns;     // ancestors (incl. the parent) in whose SECOND child the node lies
     float         cLo, cHi;       // centroid bounds on `axis`
     Box           box;
 };
@@ -83,6 +86,34 @@ struct Prim
     float4 lo; // box.lo.xyz, centroid.x
     float4 hi; // box.hi.xyz, centroid.y
     float  cz; // centroid.z
+};
+
+// Where the decide / sweep steps put what they create beyond the node records (all optional).
+struct BuildSinks
+{
+    std::uint32_t* leafStart = nullptr;     // [n + 1]: 1 at the first position of every leaf (closed-form numbering, see preorderOf)
+    std::uint32_t* created = nullptr;       // list of the node slots created (a block that builds a subtree on its own collects its next level here)
+    std::uint32_t* createdCount = nullptr;
+    std::uint32_t* deferList = nullptr;     // decide: nodes with at most deferMaxPrims primitives are not decided but appended here
+    std::uint32_t* deferCount = nullptr;
+    std::uint32_t  deferMaxPrims = 0;
+};
+
+// The exclusive scan of the partition flags as the pair / permute steps read it: plain (level-by-level path), with the offset of
+// the slice a position lies in added on the fly (single-launch build: every block scans one slice), or with the value at the end
+// of a subtree's range held aside (a block that builds a subtree on its own must not write the position after its range).
+struct ScanView
+{
+    const unsigned long long* scan = nullptr;
+    const unsigned long long* slicePrefix = nullptr;
+    std::uint32_t             slice = 1;
+    std::uint32_t             endPos = 0xFFFFFFFFu;
+    unsigned long long        endValue = 0;
+    __device__ __forceinline__ unsigned long long at(const std::uint32_t i) const
+    {
+        if (i == endPos) return endValue;
+        return scan[i] + (slicePrefix ? slicePrefix[i / slice] : 0ull);
+    }
 };
 
 // float <-> uint32 that orders like the float (negative values reversed below the positive ones).
@@ -145,8 +176,8 @@ __global__ void k_bvh_root(BuildNode* nodes, NodeAccum* accum, const std::uint32
 
 // ---- boxes: fold every primitive of an open node into the node's accumulators ------------------------------------
 // (called by whole warps: lane L handles position i = warpBase + L)
-__device__ __forceinline__ void boxesAt(const std::uint32_t i, const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* order,
-                                        const std::uint32_t* owner, NodeAccum* accum)
+__device__ __forceinline__ void boxesAt(const std::uint32_t i, const std::uint32_t n, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
+                                        const std::uint32_t* __restrict__ owner, NodeAccum* __restrict__ accum)
 {
     const std::uint32_t node = i < n ? owner[i] : NONE;
     const bool          active = node != NONE;
@@ -186,7 +217,8 @@ __global__ void k_bvh_boxes(const std::uint32_t n, const Prim* __restrict__ prim
 
 // ---- decide: leaf / two-primitive median split / SAH (bvh.cpp:96-140) --------------------------------------------
 __device__ __forceinline__ void decideAt(const std::uint32_t s, BuildNode* nodes, NodeAccum* accum, BucketAccum* buckets, const Prim* __restrict__ prims,
-                                         std::uint32_t* order, std::uint32_t* owner, std::uint32_t* counters /* [0] node slots, [1] bucket slots of this level */)
+                                         std::uint32_t* order, std::uint32_t* owner, std::uint32_t* nodeCounter /* node slots */,
+                                         std::uint32_t* bucketCounter /* bucket slots of this level */, const BuildSinks sinks = BuildSinks{})
 {
     BuildNode        nd = nodes[s];
     const NodeAccum& a = accum[s];
@@ -218,27 +250,41 @@ __device__ __forceinline__ void decideAt(const std::uint32_t s, BuildNode* nodes
     {
         nd.kind = KIND_LEAF;
         for (std::uint32_t i = nd.begin; i < nd.end; ++i) owner[i] = NONE; // (leaves with many primitives are rare)
+        if (sinks.leafStart) sinks.leafStart[nd.begin] = 1u;
+    }
+    else if (sinks.deferList && count <= sinks.deferMaxPrims)
+    {
+        // a small subtree: its primitives leave the level-by-level flow, one block will build it on its own
+        nd.kind = KIND_DEFERRED;
+        sinks.deferList[atomicAdd(sinks.deferCount, 1u)] = s;
+        for (std::uint32_t i = nd.begin; i < nd.end; ++i) owner[i] = NONE;
     }
     else if (count < 3u)
     {
         // std::nth_element over two elements: insertion sort, i.e. swap when the second compares less (bvh.cpp:124-137)
         const std::uint32_t p0 = order[nd.begin], p1 = order[nd.begin + 1u];
         if (centroidOf(prims[p1], nd.axis) < centroidOf(prims[p0], nd.axis)) order[nd.begin] = p1, order[nd.begin + 1u] = p0;
-        const std::uint32_t c = atomicAdd(&counters[0], 2u);
+        const std::uint32_t c = atomicAdd(nodeCounter, 2u);
         nd.kind = KIND_SPLIT2, nd.mid = nd.begin + 1u, nd.child0 = c, nd.child1 = c + 1u;
         BuildNode child{};
         child.kind = KIND_OPEN, child.child0 = NONE, child.child1 = NONE;
-        child.begin = nd.begin, child.end = nd.mid;
+        child.depth = nd.depth + 1u;
+        child.begin = nd.begin, child.end = nd.mid, child.rightTurns = nd.rightTurns;
         nodes[c] = child;
-        child.begin = nd.mid, child.end = nd.end;
+        child.begin = nd.mid, child.end = nd.end, child.rightTurns = nd.rightTurns + 1u;
         nodes[c + 1u] = child;
         resetAccum(accum[c]), resetAccum(accum[c + 1u]);
         owner[nd.begin] = c, owner[nd.begin + 1u] = c + 1u;
+        if (sinks.created)
+        {
+            const std::uint32_t at = atomicAdd(sinks.createdCount, 2u);
+            sinks.created[at] = c, sinks.created[at + 1u] = c + 1u;
+        }
     }
     else
     {
         nd.kind = KIND_SAH;
-        nd.bucketSlot = atomicAdd(&counters[1], 1u);
+        nd.bucketSlot = atomicAdd(bucketCounter, 1u);
         BucketAccum& b = buckets[nd.bucketSlot];
         for (std::size_t k = 0; k < BVH_NUM_BUCKETS; ++k)
         {
@@ -252,12 +298,12 @@ __global__ void k_bvh_decide(const std::uint32_t levelBegin, const std::uint32_t
                              BucketAccum* buckets, const Prim* __restrict__ prims, std::uint32_t* order, std::uint32_t* owner, std::uint32_t* counters)
 {
     const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < levelEnd) decideAt(s, nodes, accum, buckets, prims, order, owner, counters);
+    if (s < levelEnd) decideAt(s, nodes, accum, buckets, prims, order, owner, &counters[0], &counters[1]);
 }
 
 // ---- buckets: count and bound the primitives of every SAH node per bucket (bvh.cpp:146-156) ----------------------
-__device__ __forceinline__ void bucketsAt(const std::uint32_t i, const Prim* __restrict__ prims, const std::uint32_t* order,
-                                          const std::uint32_t* owner, const BuildNode* nodes, BucketAccum* buckets)
+__device__ __forceinline__ void bucketsAt(const std::uint32_t i, const Prim* __restrict__ prims, const std::uint32_t* __restrict__ order,
+                                          const std::uint32_t* __restrict__ owner, const BuildNode* __restrict__ nodes, BucketAccum* __restrict__ buckets)
 {
     const std::uint32_t s = owner[i];
     if (s == NONE) return;
@@ -282,7 +328,7 @@ __global__ void k_bvh_buckets(const std::uint32_t n, const Prim* __restrict__ pr
 
 // ---- sweep: the SAH decision of every SAH node (bvh.cpp:157-214), children for the ones that split ---------------
 __device__ __forceinline__ void sweepAt(const std::uint32_t s, BuildNode* nodes, NodeAccum* accum, const BucketAccum* buckets, std::uint32_t* owner,
-                                        std::uint32_t* counters)
+                                        std::uint32_t* nodeCounter, const BuildSinks sinks = BuildSinks{})
 {
     BuildNode nd = nodes[s];
     if (nd.kind != KIND_SAH) return;
@@ -306,20 +352,27 @@ __device__ __forceinline__ void sweepAt(const std::uint32_t s, BuildNode* nodes,
     {
         nd.kind = KIND_LEAF;
         for (std::uint32_t i = nd.begin; i < nd.end; ++i) owner[i] = NONE; // <= 255 primitives
+        if (sinks.leafStart) sinks.leafStart[nd.begin] = 1u;
     }
     else
     {
         std::uint32_t left = 0;
         for (int k = 0; k <= chosen; ++k) left += acc.count[k];
-        const std::uint32_t c = atomicAdd(&counters[0], 2u);
+        const std::uint32_t c = atomicAdd(nodeCounter, 2u);
         nd.kind = KIND_SPLIT, nd.splitBucket = static_cast<std::uint32_t>(chosen), nd.mid = nd.begin + left, nd.child0 = c, nd.child1 = c + 1u;
         BuildNode child{};
         child.kind = KIND_OPEN, child.child0 = NONE, child.child1 = NONE;
-        child.begin = nd.begin, child.end = nd.mid;
+        child.depth = nd.depth + 1u;
+        child.begin = nd.begin, child.end = nd.mid, child.rightTurns = nd.rightTurns;
         nodes[c] = child;
-        child.begin = nd.mid, child.end = nd.end;
+        child.begin = nd.mid, child.end = nd.end, child.rightTurns = nd.rightTurns + 1u;
         nodes[c + 1u] = child;
         resetAccum(accum[c]), resetAccum(accum[c + 1u]);
+        if (sinks.created)
+        {
+            const std::uint32_t at = atomicAdd(sinks.createdCount, 2u);
+            sinks.created[at] = c, sinks.created[at + 1u] = c + 1u;
+        }
     }
     nodes[s] = nd;
 }
@@ -327,7 +380,7 @@ __global__ void k_bvh_sweep(const std::uint32_t levelBegin, const std::uint32_t 
                             const BucketAccum* __restrict__ buckets, std::uint32_t* owner, std::uint32_t* counters)
 {
     const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < levelEnd) sweepAt(s, nodes, accum, buckets, owner, counters);
+    if (s < levelEnd) sweepAt(s, nodes, accum, buckets, owner, &counters[0]);
 }
 
 // ---- partition, step 1: (fails, satisfies) flags of the predicate `bucket <= splitBucket` (bvh.cpp:216-221) -------
@@ -358,7 +411,7 @@ __global__ void k_bvh_flags(const std::uint32_t n, const Prim* __restrict__ prim
 // right zone [mid, end): the k-th failing element of the left zone (from the left) and the k-th satisfying element
 // of the right zone (from the right) trade places — libstdc++'s std::__partition for bidirectional iterators. -------
 __device__ __forceinline__ void pairAt(const std::uint32_t i, const std::uint32_t* owner, const BuildNode* nodes, const unsigned long long* flags,
-                                       const unsigned long long* scan, std::uint32_t* slotLeft, std::uint32_t* slotRight)
+                                       const ScanView scan, std::uint32_t* slotLeft, std::uint32_t* slotRight)
 {
     const std::uint32_t s = owner[i];
     if (s == NONE) return;
@@ -367,12 +420,12 @@ __device__ __forceinline__ void pairAt(const std::uint32_t i, const std::uint32_
     const bool left = flags[i] == 1ull;
     if (i < nd.mid && !left)
     {
-        const std::uint32_t k = static_cast<std::uint32_t>((scan[i] >> 32) - (scan[nd.begin] >> 32));
+        const std::uint32_t k = static_cast<std::uint32_t>((scan.at(i) >> 32) - (scan.at(nd.begin) >> 32));
         slotLeft[nd.begin + k] = i;
     }
     else if (i >= nd.mid && left)
     {
-        const std::uint32_t k = static_cast<std::uint32_t>((scan[nd.end] & 0xFFFFFFFFull) - (scan[i + 1u] & 0xFFFFFFFFull));
+        const std::uint32_t k = static_cast<std::uint32_t>((scan.at(nd.end) & 0xFFFFFFFFull) - (scan.at(i + 1u) & 0xFFFFFFFFull));
         slotRight[nd.begin + k] = i;
     }
 }
@@ -381,11 +434,11 @@ __global__ void k_bvh_pair(const std::uint32_t n, const std::uint32_t* __restric
                            std::uint32_t* slotLeft, std::uint32_t* slotRight)
 {
     const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pairAt(i, owner, nodes, flags, scan, slotLeft, slotRight);
+    if (i < n) pairAt(i, owner, nodes, flags, ScanView{scan}, slotLeft, slotRight);
 }
 
 __device__ __forceinline__ void permuteAt(const std::uint32_t i, std::uint32_t* owner, const BuildNode* nodes, const unsigned long long* flags,
-                                          const unsigned long long* scan, const std::uint32_t* slotLeft, const std::uint32_t* slotRight,
+                                          const ScanView scan, const std::uint32_t* slotLeft, const std::uint32_t* slotRight,
                                           const std::uint32_t* orderIn, std::uint32_t* orderOut)
 {
     const std::uint32_t s = owner[i];
@@ -395,9 +448,9 @@ __device__ __forceinline__ void permuteAt(const std::uint32_t i, std::uint32_t* 
         const BuildNode& nd = nodes[s];
         const bool       left = flags[i] == 1ull;
         if (i < nd.mid && !left)
-            src = slotRight[nd.begin + static_cast<std::uint32_t>((scan[i] >> 32) - (scan[nd.begin] >> 32))];
+            src = slotRight[nd.begin + static_cast<std::uint32_t>((scan.at(i) >> 32) - (scan.at(nd.begin) >> 32))];
         else if (i >= nd.mid && left)
-            src = slotLeft[nd.begin + static_cast<std::uint32_t>((scan[nd.end] & 0xFFFFFFFFull) - (scan[i + 1u] & 0xFFFFFFFFull))];
+            src = slotLeft[nd.begin + static_cast<std::uint32_t>((scan.at(nd.end) & 0xFFFFFFFFull) - (scan.at(i + 1u) & 0xFFFFFFFFull))];
         owner[i] = i < nd.mid ? nd.child0 : nd.child1;
     }
     orderOut[i] = orderIn[src];
@@ -408,7 +461,7 @@ __global__ void k_bvh_permute(const std::uint32_t n, std::uint32_t* owner, const
                               const std::uint32_t* __restrict__ orderIn, std::uint32_t* orderOut)
 {
     const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) permuteAt(i, owner, nodes, flags, scan, slotLeft, slotRight, orderIn, orderOut);
+    if (i < n) permuteAt(i, owner, nodes, flags, ScanView{scan}, slotLeft, slotRight, orderIn, orderOut);
 }
 
 // ---- numbering: subtree sizes (deepest level first), pre-order indices (root first), node records ------------------
@@ -436,6 +489,32 @@ __global__ void k_bvh_preorder(const std::uint32_t levelBegin, const std::uint32
 {
     const std::uint32_t s = levelBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s < levelEnd) preorderAt(s, nodes);
+}
+
+// Pre-order (depth-first) index of a node in closed form.  The nodes before X in pre-order are its ancestors and the complete
+// subtrees hanging to the LEFT of the path root -> X, one per ancestor in whose second child X lies.  Those subtrees hold exactly
+// the leaves that start before X.begin — L of them —, and a binary subtree with l leaves has 2 l - 1 nodes, so
+//     preorder(X) = depth(X) + 2 L(X.begin) - rightTurns(X):
+// no pass over the levels (bottom-up sizes, top-down indices: 2 x 31 grid barriers for Sponza), just one scan of the leaf starts.
+__device__ __forceinline__ std::uint32_t preorderOf(const BuildNode& nd, const ScanView leavesBefore)
+{
+    return nd.depth + 2u * static_cast<std::uint32_t>(leavesBefore.at(nd.begin)) - nd.rightTurns;
+}
+__device__ __forceinline__ void emitClosedForm(const std::uint32_t s, const BuildNode* nodes, const ScanView leavesBefore, rf_bvh_node* out)
+{
+    const BuildNode& nd = nodes[s];
+    rf_bvh_node      o{}; // padding words are zero, as in the reference's aggregate initialisation
+    o.aabb_min[0] = nd.box.lo.x, o.aabb_min[1] = nd.box.lo.y, o.aabb_min[2] = nd.box.lo.z;
+    o.aabb_max[0] = nd.box.hi.x, o.aabb_max[1] = nd.box.hi.y, o.aabb_max[2] = nd.box.hi.z;
+    if (nd.kind == KIND_LEAF)
+    {
+        o.triangles_offset = nd.begin, o.second_child_offset = 0u, o.triangle_count = nd.end - nd.begin, o.split_axis = 0xFFFFFFFFu; // bvh.cpp:31-42
+    }
+    else
+    {
+        o.triangles_offset = 0u, o.second_child_offset = preorderOf(nodes[nd.child1], leavesBefore), o.triangle_count = 0u, o.split_axis = nd.axis; // bvh.cpp:44-55
+    }
+    out[preorderOf(nd, leavesBefore)] = o;
 }
 
 __device__ __forceinline__ void emitAt(const std::uint32_t s, const BuildNode* nodes, rf_bvh_node* out)
@@ -493,15 +572,33 @@ __device__ __forceinline__ unsigned long long __reduce_max_sync_u64(const unsign
 // all of it launch latency and synchronisation).  Here every phase is a grid-stride loop of the same device functions inside
 // one kernel whose blocks are all resident, separated by a grid-wide barrier (~2 us instead of a launch boundary), and the
 // level bookkeeping stays on the device.  The partition's scan is done in place: every block scans its contiguous slice of
-// the flags, the slice totals (one per block) are summed by each block for itself.
+// the flags; the slice totals (one per block) are scanned by each block for itself and added on the fly (ScanView).
+//
+// Three things keep the number of grid barriers down (Sponza, 31 levels: 3.0 -> see DESIGN.md):
+//   * 7 barriers per level (boxes | decide | buckets | sweep | scan | pair | permute): the slice offsets and the level
+//     bookkeeping need none of their own;
+//   * a node with at most SUBTREE_MAX_PRIMS primitives leaves the level-by-level flow when it is decided (KIND_DEFERRED); after
+//     the last level ONE BLOCK builds each of those subtrees completely on its own, with the same device functions on the
+//     same global arrays restricted to the subtree's positions, separated by __syncthreads — the bottom half of the levels
+//     costs no grid barrier at all.  Measured alternatives: one WARP per subtree of <= 256 primitives, all subtrees at once
+//     (2.55 ms for Sponza against 2.26 ms: three more grid-wide levels, and a lane walks 8 positions per step one after the
+//     other); 2 048 primitives per block (2.69 ms: a block's time grows with the positions per thread, 0.58 ms for 1 024
+//     primitives, 1.58 ms for 2 048).  A level of a small subtree is seven dependent steps of 1.5-6 us each through L2; staging
+//     a subtree's positions in shared memory is what is left;
+//   * node numbers come from a closed form (preorderOf) instead of a bottom-up and a top-down pass over the levels.
+constexpr std::uint32_t SUBTREE_MAX_PRIMS = 1024;
+constexpr std::uint32_t FUSED_MAX_GRID = 1024;
+
 struct FusedControl
 {
     unsigned int  barrier;      // grid barrier: arrivals so far (monotonic)
-    std::uint32_t numLevels;    // levels built
+    std::uint32_t numLevels;    // levels built by the whole grid
     std::uint32_t numNodes;
     std::uint32_t error;        // 1: more than MAX_LEVELS levels
-    unsigned long long phaseNs[12]; // time block 0 spent in each phase incl. its barrier (diagnostics): boxes, decide, buckets, sweep, scan, offsets, pair,
-                                    // permute, level bookkeeping, numbering, emit
+    std::uint32_t deferCount;   // subtrees handed to single blocks
+    std::uint32_t deferCursor[2];
+    unsigned long long phaseNs[12]; // time block 0 spent in each phase incl. its barrier (diagnostics): boxes, decide, buckets, sweep, scan, -, pair,
+                                    // permute, -, leaf scan, emit, block-local subtrees
 };
 constexpr std::uint32_t FUSED_MAX_LEVELS = 4096;
 
@@ -520,16 +617,54 @@ __device__ __forceinline__ void gridBarrier(FusedControl* ctl, unsigned int& gen
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
+// Exclusive scan over the positions [begin, end) by one block: value(i) -> scanOut[i] (relative to `begin`), and flagsOut[i] =
+// value(i) if flagsOut is given.  Returns the total (to every thread).  Both 32-bit halves of a value stay below 2^32.
+template<class Value>
+__device__ __forceinline__ unsigned long long blockScanRange(const std::uint32_t begin, const std::uint32_t end, const Value value, unsigned long long* flagsOut,
+                                                             unsigned long long* scanOut, unsigned long long* warpSums, unsigned long long* carry)
+{
+    if (threadIdx.x == 0) *carry = 0ull;
+    __syncthreads();
+    for (std::uint32_t base = begin; base < end; base += BUILD_THREADS)
+    {
+        const std::uint32_t      i = base + threadIdx.x;
+        const unsigned long long f = i < end ? value(i) : 0ull;
+        unsigned long long       incl = f;
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((threadIdx.x & 31u) >= static_cast<unsigned>(d)) incl += up;
+        }
+        if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned long long before = *carry;
+        for (std::uint32_t wIdx = 0; wIdx < (threadIdx.x >> 5); ++wIdx) before += warpSums[wIdx];
+        if (i < end)
+        {
+            if (flagsOut) flagsOut[i] = f;
+            scanOut[i] = before + incl - f;
+        }
+        __syncthreads();
+        if (threadIdx.x == BUILD_THREADS - 1) *carry = before + incl;
+        __syncthreads();
+    }
+    return *carry;
+}
+
+__global__ void __launch_bounds__(BUILD_THREADS, 2) k_bvh_build_fused(
     const rf_positions* __restrict__ tris, const std::uint32_t n, Prim* prims, std::uint32_t* order0, std::uint32_t* order1, std::uint32_t* owner,
     std::uint32_t* slotLeft, std::uint32_t* slotRight, std::uint32_t* counters, BuildNode* nodes, NodeAccum* accum, BucketAccum* buckets,
     unsigned long long* flags, unsigned long long* scan, unsigned long long* blockTotals, std::uint32_t* levelStart, FusedControl* ctl, rf_bvh_node* out,
-    unsigned long long* triangleIndices)
+    unsigned long long* triangleIndices, std::uint32_t* leafStart, std::uint32_t* deferList)
 {
     __shared__ unsigned long long warpSums[BUILD_THREADS / 32];
     __shared__ unsigned long long sliceCarry;
+    __shared__ unsigned long long slicePrefix[FUSED_MAX_GRID]; // exclusive scan of the blocks' slice totals
     __shared__ BucketAccum        blockBuckets;
     __shared__ NodeAccum          blockAccum;
+    // a block building a subtree on its own: node slots of the current / next level, their counts, the level's bucket slots
+    __shared__ std::uint32_t      localLevel[2][SUBTREE_MAX_PRIMS];
+    __shared__ std::uint32_t      localCount[2], localBucketCount, localSubtree;
     unsigned int        generation = 0;
     const std::uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     unsigned long long  phaseStart = 0;
@@ -547,6 +682,10 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
             phaseStart = t;
         }
     };
+    // the blocks' slice totals (blockTotals, complete after a grid barrier) -> their exclusive scan in shared memory
+    const auto scanSliceTotals = [&]() {
+        blockScanRange(0u, gridDim.x, [&](const std::uint32_t b) { return blockTotals[b]; }, nullptr, slicePrefix, warpSums, &sliceCarry);
+    };
     const std::uint32_t nPadded = (n + 31u) & ~31u;
 
     // primitives and the root (k_bvh_prims, k_bvh_root)
@@ -560,6 +699,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
         order0[i] = i;
         owner[i] = 0u;
     }
+    for (std::uint32_t i = tid; i <= n; i += stride) leafStart[i] = 0u;
     if (tid == 0)
     {
         BuildNode root{};
@@ -578,6 +718,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
     // contiguous slice of the positions [0, n] (n + 1 flags: the last one is the scan's total) every block scans
     const std::uint32_t slice = (n + 1u + gridDim.x - 1u) / gridDim.x;
     const std::uint32_t sliceBegin = min(blockIdx.x * slice, n + 1u), sliceEnd = min(sliceBegin + slice, n + 1u);
+    BuildSinks          levelSinks;
+    levelSinks.leafStart = leafStart, levelSinks.deferList = deferList, levelSinks.deferCount = &ctl->deferCount, levelSinks.deferMaxPrims = SUBTREE_MAX_PRIMS;
     while (levelBegin != levelEnd)
     {
         // boxes (same remark as for the buckets below: a round that lies in one node is folded in shared memory first)
@@ -625,7 +767,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
             __syncthreads();
         }
         endPhase(0);
-        for (std::uint32_t s = levelBegin + tid; s < levelEnd; s += stride) decideAt(s, nodes, accum, buckets, prims, order, owner, counters);
+        for (std::uint32_t s = levelBegin + tid; s < levelEnd; s += stride) decideAt(s, nodes, accum, buckets, prims, order, owner, &counters[0], &counters[1], levelSinks);
         endPhase(1);
         // buckets.  The 256 consecutive positions a block handles per round mostly lie in ONE node while nodes are large, and
         // then all 256 threads would hammer the same 84 accumulator words in L2 (measured: 2.4 of 5.3 ms for Sponza): such a
@@ -676,58 +818,28 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
             __syncthreads();
         }
         endPhase(2);
-        for (std::uint32_t s = levelBegin + tid; s < levelEnd; s += stride) sweepAt(s, nodes, accum, buckets, owner, counters);
+        for (std::uint32_t s = levelBegin + tid; s < levelEnd; s += stride) sweepAt(s, nodes, accum, buckets, owner, &counters[0], levelSinks);
         endPhase(3);
         // flags + exclusive scan of this block's slice (relative to the slice), slice total
-        if (threadIdx.x == 0) sliceCarry = 0ull;
-        __syncthreads();
-        for (std::uint32_t base = sliceBegin; base < sliceEnd; base += BUILD_THREADS)
         {
-            const std::uint32_t      i = base + threadIdx.x;
-            const unsigned long long f = i < sliceEnd ? flagAt(i, n, prims, order, owner, nodes) : 0ull;
-            // inclusive scan of the tile: within the warp, then across the warps (both halves of f are < 2^32: no carries cross)
-            unsigned long long incl = f;
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if ((threadIdx.x & 31u) >= static_cast<unsigned>(d)) incl += up;
-            }
-            if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            unsigned long long before = sliceCarry;
-            for (std::uint32_t wIdx = 0; wIdx < (threadIdx.x >> 5); ++wIdx) before += warpSums[wIdx];
-            if (i < sliceEnd)
-            {
-                flags[i] = f;
-                scan[i] = before + incl - f;
-            }
-            __syncthreads();
-            if (threadIdx.x == BUILD_THREADS - 1) sliceCarry = before + incl;
-            __syncthreads();
+            const unsigned long long total = blockScanRange(
+                sliceBegin, sliceEnd, [&](const std::uint32_t i) { return flagAt(i, n, prims, order, owner, nodes); }, flags, scan, warpSums, &sliceCarry);
+            if (threadIdx.x == 0) blockTotals[blockIdx.x] = total;
         }
-        if (threadIdx.x == 0) blockTotals[blockIdx.x] = sliceCarry;
         endPhase(4);
-        // offset of the slice = totals of the slices before it; make the scan global
-        {
-            unsigned long long mine = 0ull;
-            for (std::uint32_t b = threadIdx.x; b < blockIdx.x; b += BUILD_THREADS) mine += blockTotals[b];
-            for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
-            if ((threadIdx.x & 31u) == 0u) warpSums[threadIdx.x >> 5] = mine;
-            __syncthreads();
-            unsigned long long offset = 0ull;
-            for (int wIdx = 0; wIdx < BUILD_THREADS / 32; ++wIdx) offset += warpSums[wIdx];
-            for (std::uint32_t i = sliceBegin + threadIdx.x; i < sliceEnd; i += BUILD_THREADS) scan[i] += offset;
-        }
-        endPhase(5);
-        for (std::uint32_t i = tid; i < n; i += stride) pairAt(i, owner, nodes, flags, scan, slotLeft, slotRight);
+        scanSliceTotals(); // (offset of a slice = totals of the slices before it, added on the fly by ScanView::at)
+        ScanView view;
+        view.scan = scan, view.slicePrefix = slicePrefix, view.slice = slice;
+        for (std::uint32_t i = tid; i < n; i += stride) pairAt(i, owner, nodes, flags, view, slotLeft, slotRight);
         endPhase(6);
-        for (std::uint32_t i = tid; i < n; i += stride) permuteAt(i, owner, nodes, flags, scan, slotLeft, slotRight, order, orderNext);
+        for (std::uint32_t i = tid; i < n; i += stride) permuteAt(i, owner, nodes, flags, view, slotLeft, slotRight, order, orderNext);
         {
             std::uint32_t* t = order;
             order = orderNext, orderNext = t;
         }
         endPhase(7);
-        // next level: the node slots created by this one
+        // next level: the node slots created by this one.  (No barrier of its own: the counter changes again in the next level's
+        // decide step, i.e. after the next barrier, which every block reaches only after it has read the counter here.)
         const std::uint32_t created = *reinterpret_cast<volatile std::uint32_t*>(&counters[0]);
         ++level;
         if (tid == 0)
@@ -741,32 +853,103 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_bvh_build_fused(
             if (tid == 0) ctl->error = 1u;
             break;
         }
-        endPhase(8);
     }
-    if (tid == 0) ctl->numLevels = level, ctl->numNodes = levelEnd;
-    const std::uint32_t numNodes = levelEnd;
+    if (tid == 0) ctl->numLevels = level;
     gridBarrier(ctl, generation);
     if (tid == 0) phaseStart = now();
-    // numbering: sizes bottom-up, pre-order top-down, records
-    for (std::uint32_t l = level; l-- > 0u;)
+
+    // ---- the deferred subtrees, one block each --------------------------------------------------------------------------
     {
-        const std::uint32_t b = levelStart[l], e = l + 1u < level ? levelStart[l + 1u] : numNodes;
-        for (std::uint32_t s = b + tid; s < e; s += stride) sizeAt(s, nodes);
-        gridBarrier(ctl, generation);
+        // (two passes over the list, the larger subtrees first: the blocks then finish closer together)
+        const std::uint32_t deferred = *reinterpret_cast<volatile std::uint32_t*>(&ctl->deferCount);
+        std::uint32_t       pass = 0;
+        while (true)
+        {
+            if (threadIdx.x == 0) localSubtree = atomicAdd(&ctl->deferCursor[pass], 1u);
+            __syncthreads();
+            const std::uint32_t k = localSubtree;
+            __syncthreads();
+            if (k >= deferred)
+            {
+                if (++pass == 2u) break;
+                continue;
+            }
+            const std::uint32_t root = deferList[k];
+            const std::uint32_t b = nodes[root].begin, e = nodes[root].end;
+            if (((e - b) > SUBTREE_MAX_PRIMS / 2u) != (pass == 0u)) continue; // not this pass's size class
+            // SAH nodes of one level of this subtree hold >= 3 primitives each: slots [b / 3, e / 3) of the level-by-level flow's
+            // bucket accumulators (idle now) are this subtree's own
+            BucketAccum* const myBuckets = buckets + b / 3u;
+            __syncthreads();
+            for (std::uint32_t i = b + threadIdx.x; i < e; i += BUILD_THREADS) owner[i] = root;
+            if (threadIdx.x == 0)
+            {
+                nodes[root].kind = KIND_OPEN;
+                resetAccum(accum[root]);
+                localLevel[0][0] = root;
+                localCount[0] = 1u, localCount[1] = 0u, localBucketCount = 0u;
+            }
+            __syncthreads();
+            std::uint32_t* oc = order;
+            std::uint32_t* oo = orderNext;
+            int            cur = 0;
+            while (localCount[cur] != 0u)
+            {
+                const std::uint32_t levelNodes = localCount[cur];
+                BuildSinks          sinks;
+                sinks.leafStart = leafStart, sinks.created = localLevel[cur ^ 1], sinks.createdCount = &localCount[cur ^ 1];
+                for (std::uint32_t base = b; base < e; base += BUILD_THREADS) boxesAt(base + threadIdx.x, e, prims, oc, owner, accum);
+                __syncthreads();
+                for (std::uint32_t idx = threadIdx.x; idx < levelNodes; idx += BUILD_THREADS)
+                    decideAt(localLevel[cur][idx], nodes, accum, myBuckets, prims, oc, owner, &counters[0], &localBucketCount, sinks);
+                __syncthreads();
+                for (std::uint32_t i = b + threadIdx.x; i < e; i += BUILD_THREADS) bucketsAt(i, prims, oc, owner, nodes, myBuckets);
+                __syncthreads();
+                for (std::uint32_t idx = threadIdx.x; idx < levelNodes; idx += BUILD_THREADS)
+                    sweepAt(localLevel[cur][idx], nodes, accum, myBuckets, owner, &counters[0], sinks);
+                __syncthreads();
+                ScanView view;
+                view.scan = scan, view.endPos = e;
+                view.endValue = blockScanRange(b, e, [&](const std::uint32_t i) { return flagAt(i, e, prims, oc, owner, nodes); }, flags, scan, warpSums, &sliceCarry);
+                __syncthreads();
+                for (std::uint32_t i = b + threadIdx.x; i < e; i += BUILD_THREADS) pairAt(i, owner, nodes, flags, view, slotLeft, slotRight);
+                __syncthreads();
+                for (std::uint32_t i = b + threadIdx.x; i < e; i += BUILD_THREADS) permuteAt(i, owner, nodes, flags, view, slotLeft, slotRight, oc, oo);
+                {
+                    std::uint32_t* t = oc;
+                    oc = oo, oo = t;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) localCount[cur] = 0u, localBucketCount = 0u;
+                cur ^= 1;
+                __syncthreads();
+            }
+            if (oc != order)
+                for (std::uint32_t i = b + threadIdx.x; i < e; i += BUILD_THREADS) order[i] = oc[i];
+            __syncthreads();
+        }
     }
-    for (std::uint32_t l = 0; l < level; ++l)
-    {
-        const std::uint32_t b = levelStart[l], e = l + 1u < level ? levelStart[l + 1u] : numNodes;
-        for (std::uint32_t s = b + tid; s < e; s += stride) preorderAt(s, nodes);
-        gridBarrier(ctl, generation);
-    }
+    gridBarrier(ctl, generation);
+    const std::uint32_t numNodes = *reinterpret_cast<volatile std::uint32_t*>(&counters[0]);
     if (tid == 0)
     {
+        ctl->numNodes = numNodes;
         const unsigned long long t = now();
-        ctl->phaseNs[9] += t - phaseStart;
+        ctl->phaseNs[11] += t - phaseStart;
         phaseStart = t;
     }
-    for (std::uint32_t s = tid; s < numNodes; s += stride) emitAt(s, nodes, out);
+
+    // ---- numbering: one scan of the leaf starts (preorderOf), then the records ------------------------------------------
+    {
+        const unsigned long long total = blockScanRange(
+            sliceBegin, sliceEnd, [&](const std::uint32_t i) { return static_cast<unsigned long long>(leafStart[i]); }, nullptr, scan, warpSums, &sliceCarry);
+        if (threadIdx.x == 0) blockTotals[blockIdx.x] = total;
+    }
+    endPhase(9);
+    scanSliceTotals();
+    ScanView leavesBefore;
+    leavesBefore.scan = scan, leavesBefore.slicePrefix = slicePrefix, leavesBefore.slice = slice;
+    for (std::uint32_t s = tid; s < numNodes; s += stride) emitClosedForm(s, nodes, leavesBefore, out);
     for (std::uint32_t i = tid; i < n; i += stride) triangleIndices[order[i]] = i; // bvh.cpp:64-69
     if (tid == 0) ctl->phaseNs[10] += now() - phaseStart;
 }
@@ -872,17 +1055,20 @@ extern "C" rf_status rf_build_bvh_device(
         RF_BUILD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, k_bvh_build_fused, BUILD_THREADS, 0));
         if (blocksPerSm < 1) return setError(RF_ERROR_CUDA, "rf_build_bvh_device: the build kernel does not fit an SM");
         const int                grid = numSms * std::min(blocksPerSm, 2);
+        if (grid > static_cast<int>(FUSED_MAX_GRID)) return setError(RF_ERROR_CUDA, "rf_build_bvh_device: more resident blocks than the build kernel is laid out for");
         Buf<unsigned long long>  blockTotals;
-        Buf<std::uint32_t>       levelStartDev;
+        Buf<std::uint32_t>       levelStartDev, leafStart, deferList;
         Buf<FusedControl>        control;
         RF_BUILD_CUDA(blockTotals.allocate(static_cast<std::size_t>(grid)));
+        RF_BUILD_CUDA(leafStart.allocate(n + 1ull));
+        RF_BUILD_CUDA(deferList.allocate(n));
         RF_BUILD_CUDA(levelStartDev.allocate(FUSED_MAX_LEVELS));
         RF_BUILD_CUDA(control.allocate(1));
         RF_BUILD_CUDA(cudaMemset(control.ptr, 0, sizeof(FusedControl)));
         RF_BUILD_CUDA(cudaEventRecord(evBegin));
         k_bvh_build_fused<<<grid, BUILD_THREADS>>>(dTris.ptr, n, prims.ptr, order[0].ptr, order[1].ptr, owner.ptr, slotLeft.ptr, slotRight.ptr, counters.ptr,
                                                    nodes.ptr, accum.ptr, buckets.ptr, flags.ptr, scan.ptr, blockTotals.ptr, levelStartDev.ptr, control.ptr,
-                                                   dOut.ptr, dIndices.ptr);
+                                                   dOut.ptr, dIndices.ptr, leafStart.ptr, deferList.ptr);
         RF_BUILD_CUDA(cudaEventRecord(evEnd));
         RF_BUILD_CUDA(cudaEventSynchronize(evEnd));
         RF_BUILD_CUDA(cudaGetLastError());

@@ -40,6 +40,6 @@ for name in ("Duck", "Sponza"):
 
             phases = (C.c_float * 12)()
             levels = capi.lib().rf_build_bvh_device_last_phases(phases)
-            names = ("boxes", "decide", "buckets", "sweep", "scan", "offsets", "pair", "permute", "level", "numbering", "emit")
-            print(f"    {levels} levels; ms per phase (block 0, incl. the grid barrier): " + ", ".join(f"{k} {v:.3f}" for k, v in zip(names, phases)), flush=True)
+            names = ("boxes", "decide", "buckets", "sweep", "scan", "-", "pair", "permute", "-", "leaf scan", "emit", "block-local subtrees")
+            print(f"    {levels} grid-wide levels; ms per phase (block 0, incl. the grid barrier): " + ", ".join(f"{k} {v:.3f}" for k, v in zip(names, phases)), flush=True)
     capi.lib().rf_build_bvh_device_set_mode(0)
