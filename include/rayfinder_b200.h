@@ -453,8 +453,8 @@ rf_status rf_build_bvh_device(
  * level (round 1's path, kept for A/B timing).  Same bytes either way.  Process-wide. */
 void rf_build_bvh_device_set_mode(int32_t level_kernels);
 /* Diagnostics of the last single-launch build: milliseconds its first block spent in each phase, summed over the levels
- * (12 floats: boxes, decide, buckets, sweep, scan, offsets, pair, permute, level bookkeeping, numbering, emit, unused);
- * returns the number of levels. */
+ * (12 floats: boxes, decide, buckets, sweep, scan, -, pair, permute, -, leaf scan + node records, -, block-local subtrees);
+ * returns the number of grid-wide levels. */
 uint32_t rf_build_bvh_device_last_phases(float* out_phase_ms);
 
 /* ---- .pt container: nlrs::PtFormat + serialize/deserialize (pt-format/pt_format.hpp:18-43) ----- */
