@@ -148,7 +148,7 @@ extern "C" rf_status rf_build_bvh_device(
                                                    nodes.ptr, accum.ptr, buckets.ptr, flags.ptr, scan.ptr, blockTotals.ptr, levelStartDev.ptr, control.ptr,
                                                    leafStart.ptr, deferList.ptr);
         RF_BUILD_CUDA(cudaEventRecord(evLocal));
-        launchBvhBuildLocal(grid, nullptr, n, prims.ptr, order[0].ptr, order[1].ptr, owner.ptr, slotLeft.ptr, slotRight.ptr, counters.ptr, nodes.ptr, accum.ptr,
+        launchBvhBuildLocal(numSms * LOCAL_BLOCKS_PER_SM, nullptr, n, prims.ptr, order[0].ptr, order[1].ptr, owner.ptr, slotLeft.ptr, slotRight.ptr, counters.ptr, nodes.ptr, accum.ptr,
                             buckets.ptr, flags.ptr, scan.ptr, control.ptr, leafStart.ptr, deferList.ptr);
         RF_BUILD_CUDA(cudaEventRecord(evNumber));
         k_bvh_leaf_scan<<<grid, BUILD_THREADS>>>(n, leafStart.ptr, scan.ptr, blockTotals.ptr);

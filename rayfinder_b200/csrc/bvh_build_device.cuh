@@ -567,6 +567,10 @@ __device__ __forceinline__ unsigned long long __reduce_max_sync_u64(const unsign
 //   * node numbers come from a closed form (preorderOf) instead of a bottom-up and a top-down pass over the levels.
 constexpr std::uint32_t SUBTREE_MAX_PRIMS = 1024;
 constexpr std::uint32_t FUSED_MAX_GRID = 1024;
+#ifndef RF_BVH_LOCAL_BLOCKS
+#define RF_BVH_LOCAL_BLOCKS 2
+#endif
+constexpr int           LOCAL_BLOCKS_PER_SM = RF_BVH_LOCAL_BLOCKS; // blocks per SM of k_bvh_build_local (no grid barrier there: any grid works)
 
 struct FusedControl
 {
@@ -839,7 +843,7 @@ __global__ void __launch_bounds__(BUILD_THREADS, 2) k_bvh_build_fused(
 // with ld.global.cg in decideAt / sweepAt) was written by the block itself, i.e. through the same SM's L1, so the dependent
 // loads of a step hit L1 instead of making two or three L2 round trips each (the grid-wide flow above passes data between SMs
 // inside one launch and has to bypass L1: -Xptxas -dlcm=cg for bvh_build.cu).
-__global__ void __launch_bounds__(BUILD_THREADS, 2) k_bvh_build_local(
+__global__ void __launch_bounds__(BUILD_THREADS, LOCAL_BLOCKS_PER_SM) k_bvh_build_local(
     const std::uint32_t n, const Prim* __restrict__ prims, std::uint32_t* order0, std::uint32_t* order1, std::uint32_t* owner, std::uint32_t* slotLeft,
     std::uint32_t* slotRight, std::uint32_t* counters, BuildNode* nodes, NodeAccum* accum, BucketAccum* buckets, unsigned long long* flags,
     unsigned long long* scan, FusedControl* ctl, std::uint32_t* leafStart, const std::uint32_t* __restrict__ deferList)
