@@ -456,6 +456,8 @@ void rf_build_bvh_device_set_mode(int32_t level_kernels);
  * (12 floats: boxes, decide, buckets, sweep, scan, -, pair, permute, -, leaf scan + node records, -, block-local subtrees);
  * returns the number of grid-wide levels. */
 uint32_t rf_build_bvh_device_last_phases(float* out_phase_ms);
+/* rf_build_bvh_device keeps its device arrays (~0.5 KB per triangle) between calls; this frees them. */
+void rf_build_bvh_device_release(void);
 
 /* ---- .pt container: nlrs::PtFormat + serialize/deserialize (pt-format/pt_format.hpp:18-43) ----- */
 

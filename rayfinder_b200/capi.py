@@ -136,6 +136,7 @@ SIGNATURES = {
     "rf_build_bvh_device": (C.c_int32, [_P, C.c_uint64, C.c_int32, _P, C.POINTER(C.c_uint64), _P, C.POINTER(C.c_float)]),
     "rf_build_bvh_device_set_mode": (None, [C.c_int32]),
     "rf_build_bvh_device_last_phases": (C.c_uint32, [C.POINTER(C.c_float)]),
+    "rf_build_bvh_device_release": (None, []),
     "rf_pt_create": (C.c_int32, [C.POINTER(_P)]),
     "rf_pt_destroy": (None, [_P]),
     "rf_pt_load": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),

@@ -27,16 +27,33 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <mutex>
+
 namespace rfb200
 {
 namespace
 {
+// A device array that keeps its storage between calls and only grows (the builder's workspace, see g_workspace).
 template<typename T>
 struct Buf
 {
-    T* ptr = nullptr;
-    ~Buf() { cudaFree(ptr); }
-    cudaError_t allocate(std::size_t count) { return cudaMalloc(&ptr, std::max<std::size_t>(count, 1) * sizeof(T)); }
+    T*          ptr = nullptr;
+    std::size_t capacity = 0;
+    ~Buf() { release(); }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr, capacity = 0;
+    }
+    cudaError_t allocate(std::size_t count)
+    {
+        count = std::max<std::size_t>(count, 1);
+        if (count <= capacity) return cudaSuccess;
+        release();
+        const cudaError_t err = cudaMalloc(&ptr, count * sizeof(T));
+        if (err == cudaSuccess) capacity = count;
+        return err;
+    }
 };
 inline unsigned gridOf(std::uint64_t items) { return static_cast<unsigned>((items + BUILD_THREADS - 1) / BUILD_THREADS); }
 } // namespace
@@ -46,6 +63,31 @@ using namespace rfb200;
 
 namespace
 {
+// The builder's device arrays, kept between calls (allocating and freeing ~130 MB of them was most of a call: ~25 of 29 ms for
+// Sponza); one workspace per process, guarded by a mutex, dropped by rf_build_bvh_device_release or when the device changes.
+struct BuildWorkspace
+{
+    int                     device = -1;
+    Buf<rf_positions>       dTris;
+    Buf<Prim>               prims;
+    Buf<std::uint32_t>      order[2], owner, slotLeft, slotRight, counters, levelStartDev, leafStart, deferList;
+    Buf<BuildNode>          nodes;
+    Buf<NodeAccum>          accum;
+    Buf<BucketAccum>        buckets;
+    Buf<unsigned long long> flags, scan, dIndices, blockTotals;
+    Buf<rf_bvh_node>        dOut;
+    Buf<unsigned char>      scanTemp;
+    Buf<FusedControl>       control;
+    void release()
+    {
+        dTris.release(), prims.release(), order[0].release(), order[1].release(), owner.release(), slotLeft.release(), slotRight.release(), counters.release();
+        levelStartDev.release(), leafStart.release(), deferList.release(), nodes.release(), accum.release(), buckets.release(), flags.release(), scan.release();
+        dIndices.release(), blockTotals.release(), dOut.release(), scanTemp.release(), control.release();
+        device = -1;
+    }
+};
+BuildWorkspace g_workspace;
+std::mutex     g_workspaceMutex;
 float g_lastPhaseMs[12] = {};
 std::uint32_t g_lastLevels = 0;
 bool g_levelKernels = false; // rf_build_bvh_device_set_mode(1): the level-by-level path (one launch per phase and level), kept for A/B timing
@@ -54,6 +96,12 @@ extern "C" void rf_build_bvh_device_set_mode(std::int32_t levelKernels) { g_leve
 // Diagnostics of the last single-launch build: milliseconds block 0 spent in each phase (summed over the levels) and the
 // number of levels.  out_phase_ms has 12 entries: boxes, decide, buckets, sweep, scan, offsets, pair, permute, level
 // bookkeeping, numbering, emit, unused.
+extern "C" void rf_build_bvh_device_release(void)
+{
+    std::lock_guard<std::mutex> lock(g_workspaceMutex);
+    if (g_workspace.device >= 0 && cudaSetDevice(g_workspace.device) == cudaSuccess) g_workspace.release();
+    g_workspace.device = -1;
+}
 extern "C" std::uint32_t rf_build_bvh_device_last_phases(float* outPhaseMs)
 {
     if (outPhaseMs) std::memcpy(outPhaseMs, g_lastPhaseMs, sizeof(g_lastPhaseMs));
@@ -90,15 +138,31 @@ extern "C" rf_status rf_build_bvh_device(
 
     const std::uint32_t n = static_cast<std::uint32_t>(num_triangles);
     const std::uint64_t maxNodes = 2ull * n - 1ull;
-    Buf<rf_positions>       dTris;
-    Buf<Prim>               prims;
-    Buf<std::uint32_t>      order[2], owner, slotLeft, slotRight, counters;
-    Buf<BuildNode>          nodes;
-    Buf<NodeAccum>          accum;
-    Buf<BucketAccum>        buckets;
-    Buf<unsigned long long> flags, scan, dIndices;
-    Buf<rf_bvh_node>        dOut;
-    Buf<unsigned char>      scanTemp;
+    std::lock_guard<std::mutex> lock(g_workspaceMutex);
+    int                         currentDevice = 0;
+    RF_BUILD_CUDA(cudaGetDevice(&currentDevice));
+    BuildWorkspace& ws = g_workspace;
+    if (ws.device != currentDevice)
+    {
+        if (ws.device >= 0 && cudaSetDevice(ws.device) == cudaSuccess) ws.release();
+        RF_BUILD_CUDA(cudaSetDevice(currentDevice));
+        ws.device = currentDevice;
+    }
+    auto& dTris = ws.dTris;
+    auto& prims = ws.prims;
+    auto& order = ws.order;
+    auto& owner = ws.owner;
+    auto& slotLeft = ws.slotLeft;
+    auto& slotRight = ws.slotRight;
+    auto& counters = ws.counters;
+    auto& nodes = ws.nodes;
+    auto& accum = ws.accum;
+    auto& buckets = ws.buckets;
+    auto& flags = ws.flags;
+    auto& scan = ws.scan;
+    auto& dIndices = ws.dIndices;
+    auto& dOut = ws.dOut;
+    auto& scanTemp = ws.scanTemp;
     RF_BUILD_CUDA(dTris.allocate(n));
     RF_BUILD_CUDA(prims.allocate(n));
     RF_BUILD_CUDA(order[0].allocate(n));
@@ -123,16 +187,17 @@ extern "C" rf_status rf_build_bvh_device(
     if (!g_levelKernels)
     {
         // one persistent launch: as many blocks as are resident together (the grid barrier needs all of them running)
-        int currentDevice = 0, numSms = 0, blocksPerSm = 0;
-        RF_BUILD_CUDA(cudaGetDevice(&currentDevice));
+        int numSms = 0, blocksPerSm = 0;
         RF_BUILD_CUDA(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, currentDevice));
         RF_BUILD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, k_bvh_build_fused, BUILD_THREADS, 0));
         if (blocksPerSm < 1) return setError(RF_ERROR_CUDA, "rf_build_bvh_device: the build kernel does not fit an SM");
         const int                grid = numSms * std::min(blocksPerSm, 2);
         if (grid > static_cast<int>(FUSED_MAX_GRID)) return setError(RF_ERROR_CUDA, "rf_build_bvh_device: more resident blocks than the build kernel is laid out for");
-        Buf<unsigned long long>  blockTotals;
-        Buf<std::uint32_t>       levelStartDev, leafStart, deferList;
-        Buf<FusedControl>        control;
+        auto& blockTotals = ws.blockTotals;
+        auto& levelStartDev = ws.levelStartDev;
+        auto& leafStart = ws.leafStart;
+        auto& deferList = ws.deferList;
+        auto& control = ws.control;
         RF_BUILD_CUDA(blockTotals.allocate(static_cast<std::size_t>(grid)));
         RF_BUILD_CUDA(leafStart.allocate(n + 1ull));
         RF_BUILD_CUDA(deferList.allocate(n));
