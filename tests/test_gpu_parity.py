@@ -420,6 +420,32 @@ def test_sponza_persistent_kernel_is_exact(sponza_pt, block, slots, tail_paths, 
     assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
 
 
+@pytest.mark.parametrize("bounces,w,h,spp", [(1, 150, 70, 1), (2, 97, 61, 3), (16, 64, 48, 2), (8, 33, 5, 1)])
+def test_persistent_kernel_bounce_counts_and_ragged_frames(duck_pt, bounces, w, h, spp):
+    """One bounce (every path ends with its first shadow ray: the result-less hit-ring entry), two, sixteen (more levels than
+    the priority tells apart is not reached, but deep chains are), frames smaller than one pixel group per block, accumulation
+    over several samples: the persistent kernel equals the staged pipeline bit for bit."""
+    cam = rf.bvh_visualizer_camera(duck_pt.bvh_nodes, w, h)
+    images, stats = [], []
+    for persistent in (0, 1):
+        ren, _ = make_renderer(duck_pt, w, h, cam, spp, bounces)
+        ren.set_option("trace_kernel", 1)
+        ren.set_pipeline(1, persistent, 3, 256)
+        ren.set_tail_policy(0)
+        for _ in range(spp + 1):  # one call more than samples: the converged frame traces nothing
+            ren.render()
+        img, acc = ren.read_hdr()
+        assert acc == spp
+        images.append(img)
+        stats.append(ren.stats())
+        ren.close()
+    assert stats[0]["persistent_kernel"] == 0 and stats[1]["persistent_kernel"] == 1
+    for key in O.COUNTER_NAMES:
+        assert stats[0][key] == stats[1][key], key
+    assert stats[1]["paths"] == spp * w * h
+    assert np.array_equal(images[0].view(np.uint32), images[1].view(np.uint32))
+
+
 def test_click_to_focus_matches_reference_formula(duck_pt):
     """pt/main.cpp:198-226: ray through the cursor, rayIntersectBvh(..., 1000.f, ...), dot(hit.p - position, forward)."""
     f32 = np.float32
