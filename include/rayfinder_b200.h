@@ -305,6 +305,8 @@ rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
  *   "mega_slots"   persistent kernel: path slots per block = paths a block keeps in flight (a multiple of 32, at most four times
  *                  the block size; 0 = automatic: the block's share of the pixels, so that a small frame's paths all start at
  *                  once, or that share split into equal waves when it exceeds the maximum)
+ *   "priority_mode" persistent kernel: 0 = paths that lag behind the block's other paths are served first (the default), 1 = plain
+ *                  FIFO, 2 = lagging paths first only once the block has taken its last pixels
  *   "tail_paths"   persistent kernel: a block that has taken its last pixels and has at most n live paths left gives each ray a
  *                  whole warp (value n + 1; 1 = never; 0 = automatic: two per traversal warp)
  *   "evict_delay"  loop rounds a warp keeps its last rays before handing them to the tail launch (default 4)

@@ -144,7 +144,7 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
 }
 
 // Scheduling knobs of the persistent traversal loop (rf_renderer_set_tuning / rf_renderer_set_option change them).
-TraceTuning defaultTuning() { return TraceTuning{4u, 4u, 16u, 0u}; }
+TraceTuning defaultTuning() { return TraceTuning{4u, 4u, 16u, 0u, 0u}; }
 
 bool sameParams(const rf_render_parameters& a, const rf_render_parameters& b)
 {
@@ -1277,6 +1277,7 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
     if (value < 0 || value > (1ll << 30)) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: value of '%s' out of range", name);
     if (key == "shade_wait") r->tuning.shadeWait = static_cast<std::uint32_t>(value);
     else if (key == "tail_paths") r->tuning.tailPaths = static_cast<std::uint32_t>(value);
+    else if (key == "priority_mode" && value <= 2) r->tuning.priorityMode = static_cast<std::uint32_t>(value);
     else if (key == "evict_delay") r->evictDelay = static_cast<std::uint32_t>(value);
     else if (key == "trace_stack") r->forcedStackEntries = static_cast<std::uint32_t>(std::min<std::int64_t>(value, RF_STACK_SIZE));
     else if (key == "trace_kernel" && value <= 2) r->traceKernel = static_cast<int>(value);

@@ -117,6 +117,7 @@ struct TraceTuning
     std::uint32_t triMin;    // run a triangle round once this many lanes have a triangle pending
     std::uint32_t refillMin; // refill once this many lanes are idle
     std::uint32_t shadeWait; // persistent kernel: 0.5 us naps the shading warp takes to let a batch of 32 fill (mega.cuh)
+    std::uint32_t priorityMode; // persistent kernel: which paths its ready rings serve first (mega.cuh)
     std::uint32_t tailPaths; // persistent kernel: a block with this many live paths or fewer (and no pixels left to take) gives each of its rays a whole warp
 };
 
