@@ -551,7 +551,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             pipeline = (f"{stats['sub_frames']} tile set(s) on separate CUDA streams, one launch per stage (raygen, {bounces + 1} x trace, "
                         f"{bounces} x shade, accumulate per set)"
                         + (f"; each trace launch hands warps left with <= {stats['evict_max']} rays to a warp-per-ray tail launch"
-                           if stats["evict_max"] else ""))
+                           if stats["evict_max"] else "; once a launch's queue is dry a warp left with one ray walks it with all 32 lanes in place"))
         partition = (f"32x32 tiles, (tx+ty) % {world}; exchange per step: "
                      + ("owned pixels stored into rank 0's double-buffered exchange target over NVLink peer memory by the accumulation "
                         "kernel + a 4-byte all-reduce as frame barrier" if exchange_mode == "p2p"

@@ -295,8 +295,9 @@ rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t p
  * with <= evict_max rays keeps them for four more loop rounds (most of them are short and end there), then writes the
  * traversal state of the rest to a device buffer and exits; a follow-up launch gives each of those rays a whole warp
  * (32 consecutive nodes loaded and slab-tested per memory round trip, csrc/straggler.cuh), which walks the long ones
- * ~2.5x faster than a lone lane can.  0 = off (every ray ends on the lane it started on), -1 = automatic (the default: 8 when this
- * GPU owns at most ~0.6 M pixels — launches that are mostly tail — else off), up to 32. */
+ * ~2.5x faster than a lone lane can.  0 = off (every ray ends on the lane it started on), -1 = automatic (the default: off while
+ * the option "walk_in_place" is on — a warp then walks its last ray in place, which measured faster than handing it over —, else
+ * 8 when this GPU owns at most ~0.6 M pixels), up to 32. */
 rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
 /* Named scheduling / debugging knobs (results never depend on them; unknown names are an error):
  *   "shade_wait"   persistent kernel: 0.5 us naps its shading warp takes to let a batch of 32 hits fill (default 16)
@@ -305,6 +306,8 @@ rf_status rf_renderer_set_tail_policy(rf_renderer* r, int32_t evict_max);
  *   "mega_slots"   persistent kernel: path slots per block = paths a block keeps in flight (a multiple of 32, at most four times
  *                  the block size; 0 = automatic: the block's share of the pixels, so that a small frame's paths all start at
  *                  once, or that share split into equal waves when it exceeds the maximum)
+ *   "walk_in_place" staged pipeline: 1 (default) = once a traversal launch's queue is dry, a warp left with ONE ray walks it with
+ *                  all 32 lanes through 32-node windows, in place (csrc/straggler.cuh traceWarpRay); 0 = the ray ends on its lane
  *   "priority_mode" persistent kernel: 0 = paths that lag behind the block's other paths are served first (the default), 1 = plain
  *                  FIFO, 2 = lagging paths first only once the block has taken its last pixels
  *   "tail_paths"   persistent kernel: a block that has taken its last pixels and has at most n live paths left gives each ray a

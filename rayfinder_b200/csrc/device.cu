@@ -144,7 +144,7 @@ rf_status validateBvh(const rf_bvh_node* nodes, std::uint64_t numNodes, std::uin
 }
 
 // Scheduling knobs of the persistent traversal loop (rf_renderer_set_tuning / rf_renderer_set_option change them).
-TraceTuning defaultTuning() { return TraceTuning{4u, 4u, 16u, 0u, 0u}; }
+TraceTuning defaultTuning() { return TraceTuning{4u, 4u, 16u, 0u, 1u, 0u}; }
 
 bool sameParams(const rf_render_parameters& a, const rf_render_parameters& b)
 {
@@ -489,7 +489,13 @@ struct rf_renderer
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) ++ownedTileCount;
-        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : (useMega() ? 1 : 2);
+        // Automatic number of tile sets: 1 for the persistent kernel; for the staged pipeline 2 (one set's launch tails overlap the
+        // other's work) — except between ~1.2 M and ~3 M owned pixels while warps walk their last rays in place (tuning.walkInPlace):
+        // the tails are short then, and one set of full-size launches measured faster at 1920x1080 (15.86 vs 15.94 ms; at
+        // 1024^2 and 3840x2160 two sets stay ahead by ~1 %).
+        const std::uint64_t ownedPixels = static_cast<std::uint64_t>(ownedTileCount) * TILE_PIXELS;
+        const bool          oneStagedSet = tuning.walkInPlace != 0u && ownedPixels > 1200000ull && ownedPixels <= 3000000ull;
+        numSubFrames = requestedSubFrames > 0 ? requestedSubFrames : (useMega() || oneStagedSet ? 1 : 2);
         for (std::uint32_t ty = 0; ty < tilesY; ++ty)
             for (std::uint32_t tx = 0; tx < tilesX; ++tx)
                 if ((tx + ty) % world == rank) owned[k++ % static_cast<std::uint32_t>(numSubFrames)].push_back(ty * tilesX + tx);
@@ -566,7 +572,9 @@ struct rf_renderer
     std::uint32_t effectiveEvictMax() const
     {
         if (usePairs() && !useMega()) return 0u;
-        return evictMax >= 0 ? static_cast<std::uint32_t>(evictMax) : (smallFrame() ? 8u : 0u);
+        // automatic: off while warps walk their last ray in place (tuning.walkInPlace, the default: measured 1200 vs 1152 Mrays/s at
+        // 672x384 with the hand-over on top); without it, 8 for a small frame
+        return evictMax >= 0 ? static_cast<std::uint32_t>(evictMax) : (smallFrame() && tuning.walkInPlace == 0u ? 8u : 0u);
     }
 };
 
@@ -1277,6 +1285,7 @@ extern "C" rf_status rf_renderer_set_option(rf_renderer* r, const char* name, st
     if (value < 0 || value > (1ll << 30)) return setError(RF_ERROR_INVALID_ARGUMENT, "rf_renderer_set_option: value of '%s' out of range", name);
     if (key == "shade_wait") r->tuning.shadeWait = static_cast<std::uint32_t>(value);
     else if (key == "tail_paths") r->tuning.tailPaths = static_cast<std::uint32_t>(value);
+    else if (key == "walk_in_place" && value <= 1) r->tuning.walkInPlace = static_cast<std::uint32_t>(value);
     else if (key == "priority_mode" && value <= 2) r->tuning.priorityMode = static_cast<std::uint32_t>(value);
     else if (key == "evict_delay") r->evictDelay = static_cast<std::uint32_t>(value);
     else if (key == "trace_stack") r->forcedStackEntries = static_cast<std::uint32_t>(std::min<std::int64_t>(value, RF_STACK_SIZE));

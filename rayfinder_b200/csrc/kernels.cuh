@@ -382,6 +382,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_shade(
 struct TraceIO : CursorSource
 {
     static constexpr bool HANDS_OVER_STRAGGLERS = true; // at run time: stragglers.evictMax != 0
+    // k_trace goes on with the whole warp once the queue is dry and the warp holds a single ray (run time: tuning.walkInPlace)
+    static constexpr bool WALKS_LAST_RAY_WITH_WARP = true;
+    __device__ __forceinline__ bool tailPhase(const bool queueDry) const { return queueDry && scene.tuning.walkInPlace != 0u; }
     const StragglerBuffer stragglers;
     const FrameParams&  fp;
     const SceneDevice&  scene;
@@ -471,7 +474,17 @@ __global__ void __launch_bounds__(BLOCK, RF_TRACE_MIN_BLOCKS * 256 / BLOCK) k_tr
     const std::uint32_t numShadow = shadowCount ? *shadowCount : 0u;
     TraceIO io{{fetchCursor, numClosest + numShadow}, stragglers, fp, scene, closestQueue, numClosest, hits, shadowQueue, radiance,
                   v3(fp.sky.sun_direction), blockStats};
-    traceRays<2, VARIANT, BLOCK, TraceIO, STACK>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io);
+    // (the stacks are declared here so that a warp's own stack memory can serve as the scratch of its last ray's walk)
+    __shared__ __align__(128) std::uint32_t stackMemory[STACK * BLOCK];
+    static_assert(STACK * 128 >= static_cast<int>(sizeof(StragglerWindowShared)) && offsetof(StragglerWindowShared, stack) == 8 * 128, "the walk's scratch is the warp's own stack memory");
+    WarpRay leftover;
+    traceRays<2, VARIANT, BLOCK, TraceIO, STACK, true>(scene.nodes, scene.tris, scene.ordered, scene.tuning, io, stackMemory, &leftover);
+    if (leftover.state != 0)
+    {
+        // the queue is dry and this warp held one ray: all 32 lanes walk it through 32-node windows (straggler.cuh), in place
+        std::uint32_t parity = 0;
+        traceWarpRay<STRAGGLER_DIRECT>(scene.nodes, scene.tris, leftover, *reinterpret_cast<StragglerWindowShared*>(stackMemory + (threadIdx.x >> 5) * (STACK * 32)), parity, io);
+    }
     __syncthreads();
     if (threadIdx.x < 6 && blockStats[threadIdx.x] != 0u)
     {

@@ -118,6 +118,7 @@ struct TraceTuning
     std::uint32_t refillMin; // refill once this many lanes are idle
     std::uint32_t shadeWait; // persistent kernel: 0.5 us naps the shading warp takes to let a batch of 32 fill (mega.cuh)
     std::uint32_t priorityMode; // persistent kernel: which paths its ready rings serve first (mega.cuh)
+    std::uint32_t walkInPlace; // staged pipeline: 1 = once a launch's queue is dry, a warp left with ONE ray walks it with all 32 lanes (kernels.cuh, k_trace)
     std::uint32_t tailPaths; // persistent kernel: a block with this many live paths or fewer (and no pixels left to take) gives each of its rays a whole warp
 };
 
@@ -608,7 +609,7 @@ __device__ __forceinline__ void traceRays(
             // at most ONE ray leaves this loop, and its caller goes on ray by ray with all 32 lanes (straggler.cuh: 32-node
             // windows, ~2.5x faster than a lone lane).  The ray's state leaves through `leftover` (shuffles), its stack through
             // the first 32 words of row 8 of the warp's own stack memory (where StragglerWindowShared::stack lies).
-            if (sceneOrdered && io.tailPhase())
+            if (sceneOrdered && io.tailPhase(exhausted))
             {
                 const unsigned walking = __ballot_sync(0xFFFFFFFFu, state == NODE || state == TRI);
                 const unsigned holding = __ballot_sync(0xFFFFFFFFu, state != IDLE);

@@ -352,6 +352,28 @@ def test_results_do_not_depend_on_scheduling(duck_pt, kernel, sub_frames, persis
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sub_frames,evict_max", [(1, 0), (2, 0), (2, 8)])
+def test_sponza_walk_in_place_is_exact(sponza_pt, sub_frames, evict_max):
+    """Option walk_in_place: once a staged traversal launch's queue is dry, a warp left with one ray walks it with all 32 lanes in
+    place (the ray moves from its lane to the warp in mid-traversal, through registers and the warp's own stack memory)."""
+    w, h, bounces = 480, 270, 8
+    cam = rf.fly_camera(w, h)
+    images, stats = [], []
+    for walk in (0, 1):
+        ren, _ = make_renderer(sponza_pt, w, h, cam, 2, bounces)
+        ren.set_option("trace_kernel", 1)
+        ren.set_pipeline(sub_frames, 0, 3, 256)
+        ren.set_tail_policy(evict_max)
+        ren.set_option("walk_in_place", walk)
+        ren.render(), ren.render()
+        images.append(ren.read_hdr()[0])
+        stats.append(ren.stats())
+        ren.close()
+    for key in O.COUNTER_NAMES:
+        assert stats[0][key] == stats[1][key], key
+    assert np.array_equal(images[0].view(np.uint32), images[1].view(np.uint32))
+
+
 @pytest.mark.parametrize("evict_max,sub_frames,window_mode", [(1, 1, 0), (8, 1, 0), (32, 2, 0), (-1, -1, 0), (8, 1, 1), (32, 2, 1), (-1, -1, 1)])
 def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames, window_mode):
     """The warp-per-ray tail kernel (csrc/straggler.cuh: 32-node windows, lane-parallel slab and first-triangle tests,
@@ -376,8 +398,9 @@ def test_sponza_tail_hand_over_is_exact(sponza_pt, evict_max, sub_frames, window
     ren2.render(), ren2.render()
     img, _ = ren2.read_hdr()
     stats = ren2.stats()
-    assert stats["evict_max"] == (8 if evict_max < 0 else evict_max)  # automatic: a small frame hands its tails over
-    assert stats["kernel_launches"] > ref_stats["kernel_launches"]
+    assert stats["evict_max"] == (0 if evict_max < 0 else evict_max)  # automatic: off — warps walk their last ray in place (walk_in_place)
+    if evict_max > 0:
+        assert stats["kernel_launches"] > ref_stats["kernel_launches"]
     for key in O.COUNTER_NAMES:
         assert stats[key] == ref_stats[key], key
     assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32))
