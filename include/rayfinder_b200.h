@@ -287,7 +287,8 @@ rf_status rf_renderer_set_tuning(rf_renderer* r, uint32_t tri_min, uint32_t refi
  *   ...) otherwise.
  * sub_frames (1..4, 0 keeps, -1 automatic = the default): the frame is traced as that many independent tile sets on separate
  *   CUDA streams.  Automatic: 1 with the persistent kernel; 2 with the staged pipeline, so that one set's traversal tail
- *   overlaps the other's work.
+ *   overlaps the other's work — except between ~1.2 M and ~3 M owned pixels (option "walk_in_place" on), where one set of
+ *   full-size launches measured faster.
  * variant (0..15, -1 keeps) / block_threads (64, 128, 256, 0 keeps): compile-time scheduling variant and block size of the
  *   staged traversal kernel (the persistent kernel's block size is the option "mega_block"). */
 rf_status rf_renderer_set_pipeline(rf_renderer* r, int32_t sub_frames, int32_t persistent_kernel, int32_t variant, int32_t block_threads);
